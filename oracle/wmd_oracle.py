@@ -1,0 +1,295 @@
+"""oracle/wmd_oracle.py -- TEST INFRASTRUCTURE ONLY (CPU oracle).  PARITY UNPINNED.
+
+CPU restatement of the reference's Word Mover's Distance path:
+
+* ``/root/reference/src/wmd.py:31-45``  (``WMDdistance.cal_wmd`` / ``cal_wmd_label``)
+* ``/root/reference/evaluate/auto/content_preserve.py:38-50`` (``calculate_wmd_scores``)
+
+Both bottom out in gensim 3.8.x ``KeyedVectors.wmdistance`` -> pyemd 0.5.1
+``emd`` (third-party, neither vendored under /root/reference nor installed in
+this image, no network).  Their published algorithm is restated here from the
+normative spec in SURVEY.md section 8(c) (steps S1..S6).  "Parity unpinned":
+the reference holds no tests/golden vectors for this path; the oracle is pinned
+by pyemd's known-answer vectors, two independent exact solvers and numpy's own
+float32 kernels (see tests/test_oracle_*.py).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import this module.  The product package
+``consistent__style_transfer_b200`` never does.
+
+Two implementations of the same spec live here and are tested against each
+other bit-for-bit:
+
+``KeyedVectorsOracle.wmdistance``  the per-pair Python loop shaped like gensim's
+    (per-cell ``sqrt(np.sum((a-b)**2))`` in float32 with numpy's own kernels,
+    ``Dictionary`` id order, nBOW) + the C emd_hat restatement.  This is the
+    "reference-faithful" CPU baseline that ``bench.py --impl reference`` times.
+``batch_wmd``  the all-C path (oracle/wmd_oracle.c) used to check 10^4..10^5
+    GPU results in seconds.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle_wmd.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle_wmd.so with oracle/Makefile (gcc)."""
+    srcs = [os.path.join(_HERE, f) for f in ("emd_hat.c", "wmd_oracle.c", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        try:
+            build()
+        except Exception:
+            if not os.path.exists(_LIB_PATH):
+                raise
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int)
+        lp = ctypes.POINTER(ctypes.c_longlong)
+        fp = ctypes.POINTER(ctypes.c_float)
+        L.emd_hat_gd_metric_double.restype = ctypes.c_double
+        L.emd_hat_gd_metric_double.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_double]
+        L.emd_hat_integral.restype = ctypes.c_longlong
+        L.emd_hat_integral.argtypes = [lp, lp, lp, ctypes.c_int, ctypes.c_longlong]
+        L.emd_hat_quantise.restype = None
+        L.emd_hat_quantise.argtypes = [dp, dp, dp, ctypes.c_int, lp, lp, lp]
+        L.wmd_oracle_dist_f32.restype = ctypes.c_float
+        L.wmd_oracle_dist_f32.argtypes = [fp, fp, ctypes.c_long]
+        L.wmd_oracle_batch.restype = None
+        L.wmd_oracle_batch.argtypes = [fp, ctypes.c_long, ctypes.c_long, ip, ip, lp, ip, lp,
+                                       ctypes.c_longlong, dp, ip, ctypes.c_int]
+        L.wmd_oracle_nbow.restype = ctypes.c_int
+        L.wmd_oracle_nbow.argtypes = [ip, ip, ctypes.c_int, ip, ip, dp]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+# --------------------------------------------------------------------------- #
+# pyemd.emd(first_histogram, second_histogram, distance_matrix, extra_mass_penalty=-1.0)
+# call sites: gensim wmdistance; /root/reference/evaluate/auto/transfer_intensity.py:11
+# --------------------------------------------------------------------------- #
+def emd(first_histogram, second_histogram, distance_matrix, extra_mass_penalty: float = -1.0) -> float:
+    d1 = np.ascontiguousarray(first_histogram, dtype=np.float64)
+    d2 = np.ascontiguousarray(second_histogram, dtype=np.float64)
+    D = np.ascontiguousarray(distance_matrix, dtype=np.float64)
+    n = d1.shape[0]
+    assert d2.shape == (n,) and D.shape == (n, n)
+    return float(lib().emd_hat_gd_metric_double(_p(d1, ctypes.c_double), _p(d2, ctypes.c_double),
+                                                _p(D, ctypes.c_double), n, float(extra_mass_penalty)))
+
+
+def emd_quantise(d1, d2, D):
+    """Integer problem of spec S6(a)-(d): (iP, iQ, iC) as int64 arrays."""
+    d1 = np.ascontiguousarray(d1, dtype=np.float64)
+    d2 = np.ascontiguousarray(d2, dtype=np.float64)
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    n = d1.shape[0]
+    iP = np.zeros(n, np.int64); iQ = np.zeros(n, np.int64); iC = np.zeros((n, n), np.int64)
+    lib().emd_hat_quantise(_p(d1, ctypes.c_double), _p(d2, ctypes.c_double), _p(D, ctypes.c_double), n,
+                           _p(iP, ctypes.c_longlong), _p(iQ, ctypes.c_longlong), _p(iC, ctypes.c_longlong))
+    return iP, iQ, iC
+
+
+def emd_integral(iP, iQ, iC, extra_mass_penalty: int = 0) -> int:
+    iP = np.ascontiguousarray(iP, dtype=np.int64)
+    iQ = np.ascontiguousarray(iQ, dtype=np.int64)
+    iC = np.ascontiguousarray(iC, dtype=np.int64)
+    return int(lib().emd_hat_integral(_p(iP, ctypes.c_longlong), _p(iQ, ctypes.c_longlong),
+                                      _p(iC, ctypes.c_longlong), iP.shape[0], int(extra_mass_penalty)))
+
+
+# --------------------------------------------------------------------------- #
+# gensim KeyedVectors restatement
+# --------------------------------------------------------------------------- #
+def init_sims_replace(vectors: np.ndarray) -> np.ndarray:
+    """gensim ``init_sims(replace=True)`` (called at /root/reference/src/wmd.py:54 and
+    content_preserve.py:40): in-place float32 row L2 normalisation
+    ``v /= sqrt((v**2).sum(-1))`` row by row."""
+    v = np.array(vectors, dtype=np.float32, copy=True)
+    for i in range(v.shape[0]):
+        v[i, :] /= np.sqrt((v[i, :] ** 2).sum(-1))
+    return v
+
+
+class KeyedVectorsOracle:
+    """Stands where gensim's ``model.wv`` stands: ``wv.wmdistance(doc1, doc2)``."""
+
+    def __init__(self, index2word: Sequence[str], vectors: np.ndarray, normalize: bool = False):
+        self.index2word = list(index2word)
+        self.vectors = init_sims_replace(vectors) if normalize else np.ascontiguousarray(vectors, np.float32)
+        self.vocab = {w: i for i, w in enumerate(self.index2word)}
+
+    def __contains__(self, w):
+        return w in self.vocab
+
+    def __getitem__(self, w):
+        return self.vectors[self.vocab[w]]
+
+    def wmdistance(self, document1: Iterable[str], document2: Iterable[str]) -> float:
+        # S1: drop OOV tokens
+        document1 = [t for t in document1 if t in self.vocab]
+        document2 = [t for t in document2 if t in self.vocab]
+        if len(document1) == 0 or len(document2) == 0:
+            return float("inf")
+        # S2: Dictionary(documents=[doc1, doc2]) id order
+        token2id = {}
+        for w in sorted(set(document1)):
+            token2id[w] = len(token2id)
+        for w in sorted(set(document2) - set(document1)):
+            token2id[w] = len(token2id)
+        vocab_len = len(token2id)
+        if vocab_len == 1:
+            return 0.0
+        docset1, docset2 = set(document1), set(document2)
+        # S3: float32 distances widened into a float64 matrix, python double loop
+        D = np.zeros((vocab_len, vocab_len), dtype=np.float64)
+        items = sorted((i, t) for t, i in token2id.items())
+        for i, t1 in items:
+            if t1 not in docset1:
+                continue
+            for j, t2 in items:
+                if t2 not in docset2 or D[i, j] != 0.0:
+                    continue
+                D[i, j] = D[j, i] = np.sqrt(np.sum((self[t1] - self[t2]) ** 2))
+        # S4
+        if np.sum(D) == 0.0:
+            return float("inf")
+        # S5: nBOW
+        def nbow(document):
+            d = np.zeros(vocab_len, dtype=np.float64)
+            counts = {}
+            for w in document:
+                counts[w] = counts.get(w, 0) + 1
+            doc_len = len(document)
+            for w, freq in counts.items():
+                d[token2id[w]] = freq / float(doc_len)
+            return d
+        # S6
+        return emd(nbow(document1), nbow(document2), D)
+
+
+class WMDdistanceOracle:
+    """Restates /root/reference/src/wmd.py:11-55 on top of ``KeyedVectorsOracle``."""
+
+    class _Model:
+        def __init__(self, wv):
+            self.wv = wv
+
+    def __init__(self, wv: KeyedVectorsOracle):
+        self.model = self._Model(wv)
+
+    def cal_wmd(self, x1, x2):                                   # wmd.py:31-32
+        return self.model.wv.wmdistance(x1, x2)
+
+    def cal_wmd_label(self, xs1, xs2, tokenizer):                # wmd.py:34-45
+        label = []
+        for x1, x2 in zip(xs1, xs2):
+            if len(x1) == 0 or len(x2) == 0:
+                label.append(max([float(len(x1)), float(len(x2))]))
+            else:
+                distance = self.cal_wmd(tokenizer.ids_to_tokens(x1), tokenizer.ids_to_tokens(x2))
+                if distance == float("inf"):
+                    label.append((len(x1) + len(x2)) / 2)
+                else:
+                    label.append(distance)
+        return label
+
+
+def calculate_wmd_scores(references, candidates, wmd_model, tokenize):   # content_preserve.py:43-50
+    return [wmd_model.wv.wmdistance(tokenize(references[i]), tokenize(candidates[i]))
+            for i in range(len(references))]
+
+
+# --------------------------------------------------------------------------- #
+# all-C batch path
+# --------------------------------------------------------------------------- #
+def string_rank(index2word: Sequence[str]) -> np.ndarray:
+    """rank[row] = position of the row's token in Python string order (gensim Dictionary order)."""
+    order = sorted(range(len(index2word)), key=index2word.__getitem__)
+    rank = np.empty(len(index2word), np.int32)
+    rank[np.asarray(order, dtype=np.int64)] = np.arange(len(index2word), dtype=np.int32)
+    return rank
+
+
+def batch_wmd(table: np.ndarray, ids1, off1, ids2, off2, rank: Optional[np.ndarray] = None,
+              nthreads: int = 1):
+    """WMD for CSR-packed pairs of row-id lists (-1 = OOV).  Returns (float64[B], int32 status[B])."""
+    table = np.ascontiguousarray(table, np.float32)
+    ids1 = np.ascontiguousarray(ids1, np.int32); ids2 = np.ascontiguousarray(ids2, np.int32)
+    off1 = np.ascontiguousarray(off1, np.int64); off2 = np.ascontiguousarray(off2, np.int64)
+    B = off1.shape[0] - 1
+    out = np.empty(B, np.float64); st = np.empty(B, np.int32)
+    rk = None
+    if rank is not None:
+        rank = np.ascontiguousarray(rank, np.int32)
+        rk = _p(rank, ctypes.c_int)
+    lib().wmd_oracle_batch(_p(table, ctypes.c_float), table.shape[1], table.shape[1], rk,
+                           _p(ids1, ctypes.c_int), _p(off1, ctypes.c_longlong),
+                           _p(ids2, ctypes.c_int), _p(off2, ctypes.c_longlong),
+                           B, _p(out, ctypes.c_double), _p(st, ctypes.c_int), int(nthreads))
+    return out, st
+
+
+def dist_f32(a: np.ndarray, b: np.ndarray) -> np.float32:
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return np.float32(lib().wmd_oracle_dist_f32(_p(a, ctypes.c_float), _p(b, ctypes.c_float), a.shape[0]))
+
+
+def nbow(doc_rows: Sequence[int], rank: Optional[np.ndarray] = None):
+    """(rows int32[u], counts int32[u], weights float64[u]) in canonical order; OOV (-1) dropped."""
+    doc = np.ascontiguousarray(doc_rows, np.int32)
+    n = max(1, doc.shape[0])
+    rows = np.empty(n, np.int32); cnt = np.empty(n, np.int32); w = np.empty(n, np.float64)
+    rk = None if rank is None else _p(np.ascontiguousarray(rank, np.int32), ctypes.c_int)
+    u = lib().wmd_oracle_nbow(rk, _p(doc, ctypes.c_int), doc.shape[0], _p(rows, ctypes.c_int),
+                              _p(cnt, ctypes.c_int), _p(w, ctypes.c_double))
+    return rows[:u].copy(), cnt[:u].copy(), w[:u].copy()
+
+
+# --------------------------------------------------------------------------- #
+# Relaxed WMD (not in the reference; Kusner et al. 2015, used for pruning).
+# Restated with the same float32 distances so argmins can be checked bit-exactly.
+# --------------------------------------------------------------------------- #
+def rwmd_pair(table: np.ndarray, doc1_rows: Sequence[int], doc2_rows: Sequence[int],
+              rank: Optional[np.ndarray] = None):
+    """Returns (lb, l1, l2, argmin_rows int32[u1], argmin_cols int32[u2]) or None if a side is empty.
+    lb = max(l1, l2); l1 = sum_i w1[i]*min_j D[i,j] accumulated sequentially in canonical
+    order in FP64; argmin ties -> lowest index."""
+    r1, _, w1 = nbow(doc1_rows, rank)
+    r2, _, w2 = nbow(doc2_rows, rank)
+    if len(r1) == 0 or len(r2) == 0:
+        return None
+    D = np.empty((len(r1), len(r2)), np.float32)
+    for i, a in enumerate(r1):
+        for j, b in enumerate(r2):
+            D[i, j] = dist_f32(table[a], table[b])
+    am_r = D.argmin(axis=1).astype(np.int32)
+    am_c = D.argmin(axis=0).astype(np.int32)
+    l1 = 0.0
+    for i in range(len(r1)):
+        l1 += w1[i] * float(D[i, am_r[i]])
+    l2 = 0.0
+    for j in range(len(r2)):
+        l2 += w2[j] * float(D[am_c[j], j])
+    return max(l1, l2), l1, l2, am_r, am_c
