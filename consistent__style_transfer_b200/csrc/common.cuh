@@ -1,0 +1,68 @@
+// common.cuh -- shared definitions of the sm_100a WMD kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+namespace wmd {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxDocLen = 256;          // WMD_MAX_DOC_LEN
+constexpr int kIntInf = 0x3fffffff;      // "infinite" tentative distance (sums of two stay < 2^31)
+
+// per-pair solver classes written by the nBOW kernel (meta & 7)
+constexpr int kClsNone = 0;              // nothing to do (early-out already written)
+constexpr int kClsA = 1;                 // residual rows <= 32 and columns (incl. dummy) <= 32
+constexpr int kClsB = 2;                 // <= 64 / <= 64
+constexpr int kClsC = 3;                 // anything up to 256 x 257
+constexpr int kMetaSwap = 8;             // doc2 is the heavier (supplying) side
+
+// One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).
+struct DocSide {
+    const int32_t *ids;
+    const int64_t *off;
+    int32_t L;            // padded row length when off == nullptr
+    int32_t pad_id;
+    int32_t has_pad;
+    int32_t _r;
+};
+
+__device__ __forceinline__ void doc_span(const DocSide &s, int64_t p, int64_t &start, int &len)
+{
+    if (s.off) { start = s.off[p]; len = (int)(s.off[p + 1] - start); }
+    else       { start = p * (int64_t)s.L; len = s.L; }
+}
+
+struct Vocab {
+    const float *table;       // [V, ld] float32, device
+    int64_t V;
+    int32_t d;
+    int32_t ld;               // floats between rows (multiple of 4)
+    const int32_t *map;       // tokenizer id -> row, or nullptr
+    int64_t nmap;
+    const int32_t *rank;      // row -> canonical order key, or nullptr
+};
+
+// numpy FLOAT_pairwise_sum recursion flattened to a postfix program: each op sums one leaf
+// block [start, start+len) with eight strided accumulators and pushes it; `adds` pops follow.
+constexpr int kMaxPlanOps = 64;
+struct SumPlan {
+    int32_t nops;
+    int32_t start[kMaxPlanOps];
+    int32_t len[kMaxPlanOps];
+    int32_t adds[kMaxPlanOps];
+};
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+    return __reduce_add_sync(kFull, v);
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+}  // namespace wmd

@@ -1,0 +1,275 @@
+// solve.cuh -- K3: exact transportation solver, one warp per document pair.
+//
+// Replaces pyemd's emd_hat_gd_metric<double> from the quantisation of the costs onward
+// (SURVEY.md 8(c) S4, S6(c)-(f)):  Cn = 1e6 / maxC, iC = floor(D * Cn + 0.5), the integer
+// minimum of sum f_ij * iC_ij over flows that ship the lighter side completely (the heavier
+// side's surplus leaves through a zero-cost dummy column -- value-equivalent to pyemd's
+// threshold node), and the un-normalisation  dist = opt / PQn / Cn + (maxSum - minSum) * maxC.
+//
+// pyemd runs successive shortest paths over adjacency lists; that shape is wrong for a warp.
+// Here the residual problem (m supplying rows x nc columns) lives in shared memory as dense
+// int32 cost and flow matrices and the warp runs a primal-dual (Hungarian-style) method:
+// rows are admitted one at a time, each Dijkstra runs over the dense bipartite residual graph
+// with one column (or KC columns) per lane -- relax a row = one shared-memory read per lane,
+// pick the next column = one REDUX.MIN + one ballot.  All quantities are integers below 2^31,
+// so the optimum is exact and equals the reference's regardless of the pivot path.
+#pragma once
+#include "common.cuh"
+
+namespace wmd {
+
+struct SolveArgs {
+    DocSide s1, s2;
+    int64_t p0;
+    int32_t npairs;
+    int32_t cls;                      // class this launch serves (kClsA also finalises kClsNone pairs with status 0)
+    int32_t mr, mc;                   // row / column capacity of the per-warp matrices
+    int32_t ldc;                      // column pitch (odd)
+    int32_t use_global;               // matrices in global scratch (class C)
+    int32_t *scratch;                 // [warps, 2 * mr * ldc] when use_global
+    const int32_t *ip1, *ip2;
+    const int32_t *u12, *meta;
+    const double *pqn, *extra;
+    const float *tiles;
+    int64_t tile_stride;
+    const float *maxc;
+    unsigned int *counter;            // work-claim counter for this launch (zeroed by the host)
+    double *out;
+    int32_t *status;
+};
+
+__host__ __device__ inline size_t solve_smem_per_warp(int mr, int mc, int ldc, bool use_global)
+{
+    size_t ints = (size_t)mr * 4 /* u, rowdist, rowpred, supply */ + (size_t)mr /* ridx */ + 2 * (size_t)mc /* cidx, way */;
+    if (!use_global) ints += 2 * (size_t)mr * ldc;
+    return ints * 4;
+}
+
+template <int KC>
+__device__ __forceinline__ void relax_row(const int *cost, int ldc, int nc, int row, int di, int ui, int lane,
+                                          const int (&v)[KC], unsigned used, int (&minv)[KC], int (&way)[KC])
+{
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nc && !((used >> k) & 1u)) {
+            const int cand = di + cost[row * ldc + c] - ui - v[k];
+            if (cand < minv[k]) { minv[k] = cand; way[k] = row; }
+        }
+    }
+}
+
+// Exact min-cost of shipping supply[] (rows) into deficit[] (columns; sum equal). Returns sum f*c.
+template <int KC>
+__device__ long long transport_solve(int m, int nc, int ldc, const int *cost, int *flow,
+                                     int *su, int *srowdist, int *srowpred, const int *ssupply, int *sway,
+                                     int (&deficit)[KC], int lane)
+{
+    int v[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) v[k] = 0;
+    for (int i = lane; i < m; i += kWarp) su[i] = 0;
+    for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0;
+    __syncwarp();
+
+    for (int r = 0; r < m; ++r) {
+        int sup = ssupply[r];
+        while (sup > 0) {
+            int minv[KC], way[KC];
+            unsigned used = 0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { minv[k] = kIntInf; way[k] = -1; }
+            for (int i = lane; i < m; i += kWarp) srowdist[i] = (i == r) ? 0 : -1;
+            __syncwarp();
+            relax_row<KC>(cost, ldc, nc, r, 0, su[r], lane, v, used, minv, way);
+            int D, j0, def;
+            for (;;) {
+                int best = kIntInf, bk = 0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (!((used >> k) & 1u) && minv[k] < best) { best = minv[k]; bk = k; }
+                const int delta = __reduce_min_sync(kFull, best);
+                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
+                const int jl = __ffs(__ballot_sync(kFull, best == delta)) - 1;
+                const int jk = __shfl_sync(kFull, bk, jl);
+                int mydef = 0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) if (k == jk) mydef = deficit[k];
+                def = __shfl_sync(kFull, mydef, jl);
+                if (lane == jl) used |= 1u << jk;
+                j0 = jl + 32 * jk;
+                D = delta;
+                if (def > 0) break;
+                // column j0 is saturated: every row shipping into it joins the tree at distance delta
+                for (int base = 0; base < m; base += kWarp) {
+                    const int i = base + lane;
+                    bool isnew = false;
+                    if (i < m && srowdist[i] < 0 && flow[i * ldc + j0] > 0) {
+                        isnew = true; srowdist[i] = delta; srowpred[i] = j0;
+                    }
+                    unsigned mask = __ballot_sync(kFull, isnew);
+                    while (mask) {
+                        const int b = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        relax_row<KC>(cost, ldc, nc, base + b, delta, su[base + b], lane, v, used, minv, way);
+                    }
+                }
+            }
+            // dual update: tree nodes move by (D - their distance); others keep their potentials
+            for (int i = lane; i < m; i += kWarp) {
+                const int dd = srowdist[i];
+                if (dd >= 0) su[i] += D - dd;
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if ((used >> k) & 1u) v[k] -= D - minv[k];
+                const int c = lane + 32 * k;
+                if (c < nc) sway[c] = way[k];
+            }
+            __syncwarp();
+            // augment along the tree path j0 -> ... -> r
+            int amt = min(sup, def);
+            for (int j = j0;;) {
+                const int i = sway[j];
+                if (i == r) break;
+                const int jp = srowpred[i];
+                amt = min(amt, flow[i * ldc + jp]);
+                j = jp;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int j = j0;;) {
+                    const int i = sway[j];
+                    flow[i * ldc + j] += amt;
+                    if (i == r) break;
+                    const int jp = srowpred[i];
+                    flow[i * ldc + jp] -= amt;
+                    j = jp;
+                }
+            }
+            sup -= amt;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) if (lane + 32 * k == j0) deficit[k] -= amt;
+            __syncwarp();
+        }
+    }
+    long long tot = 0;
+    for (int x = lane; x < m * ldc; x += kWarp) {
+        const int c = x % ldc;
+        if (c < nc) tot += (long long)flow[x] * (long long)cost[x];
+    }
+    return warp_sum_ll(tot);
+}
+
+template <int KC>
+__global__ void __launch_bounds__(256)
+emd_solve_kernel(const __grid_constant__ SolveArgs A)
+{
+    extern __shared__ __align__(16) int smem_i[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = solve_smem_per_warp(A.mr, A.mc, A.ldc, A.use_global) / 4;
+    int *sb = smem_i + (size_t)wib * per_warp;
+    int *su = sb, *srowdist = sb + A.mr, *srowpred = sb + 2 * A.mr, *ssupply = sb + 3 * A.mr;
+    int *sridx = sb + 4 * A.mr, *scidx = sb + 5 * A.mr, *sway = scidx + A.mc;
+    int *cost, *flow;
+    if (A.use_global) {
+        cost = A.scratch + ((size_t)blockIdx.x * wpb + wib) * 2 * (size_t)A.mr * A.ldc;
+        flow = cost + (size_t)A.mr * A.ldc;
+    } else {
+        cost = sway + A.mc;
+        flow = cost + (size_t)A.mr * A.ldc;
+    }
+    int64_t tok1, tok2;
+    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = (int)atomicAdd(A.counter, 8u);
+        q0 = __shfl_sync(kFull, q0, 0);
+        if (q0 >= A.npairs) break;
+        const int q1 = min(A.npairs, q0 + 8);
+        for (int q = q0; q < q1; ++q) {
+            const int meta = A.meta[q];
+            const int cls = meta & 7;
+            const int64_t p = A.p0 + q;
+            if (cls == kClsNone) continue;                       // early-out already written by K1
+            if (cls != A.cls) continue;
+            const float maxc_f = A.maxc[q];
+            if (!(maxc_f > 0.f)) {                               // S4: all-zero distance matrix
+                if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+                continue;
+            }
+            const int u = A.u12[q];
+            const int u1 = u & 0xffff, u2 = u >> 16;
+            const bool swap = (meta & kMetaSwap) != 0;
+            int64_t a1, a2; int l;
+            doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
+            const int32_t *ipR = swap ? A.ip2 + (a2 - tok2) : A.ip1 + (a1 - tok1);   // supplying side
+            const int32_t *ipC = swap ? A.ip1 + (a1 - tok1) : A.ip2 + (a2 - tok2);
+            const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
+            // compact the residual rows / columns
+            int m = 0, n = 0, sumR = 0, sumC = 0;
+            for (int base = 0; base < uR; base += kWarp) {
+                const int i = base + lane;
+                const int x = i < uR ? ipR[i] : 0;
+                const unsigned bal = __ballot_sync(kFull, x > 0);
+                if (x > 0) { const int pos = m + __popc(bal & ((1u << lane) - 1)); sridx[pos] = i; ssupply[pos] = x; }
+                m += __popc(bal);
+                sumR += x;
+            }
+            int deficit[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) deficit[k] = 0;
+            for (int base = 0; base < uC; base += kWarp) {
+                const int j = base + lane;
+                const int x = j < uC ? ipC[j] : 0;
+                const unsigned bal = __ballot_sync(kFull, x > 0);
+                if (x > 0) { const int pos = n + __popc(bal & ((1u << lane) - 1)); scidx[pos] = j; sway[pos] = x; /* staging */ }
+                n += __popc(bal);
+                sumC += x;
+            }
+            sumR = warp_sum(sumR); sumC = warp_sum(sumC);
+            __syncwarp();
+            long long opt = 0;
+            if (n > 0 && m > 0) {
+                const int diff = sumR - sumC;                    // >= 0 by the choice of the supplying side
+                const int nc = n + (diff > 0 ? 1 : 0);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int c = lane + 32 * k;
+                    deficit[k] = c < n ? sway[c] : (c == n && diff > 0 ? diff : 0);
+                }
+                __syncwarp();
+                // quantised costs of the residual sub-tile (S6(d)); dummy column costs 0
+                const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+                const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+                for (int rI = 0; rI < m; ++rI) {
+                    const int i = sridx[rI];
+                    for (int c = lane; c < nc; c += kWarp) {
+                        int ic = 0;
+                        if (c < n) {
+                            const int j = scidx[c];
+                            const float dv = swap ? tile[(int64_t)j * u2 + i] : tile[(int64_t)i * u2 + j];
+                            ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                        }
+                        cost[rI * A.ldc + c] = ic;
+                    }
+                }
+                __syncwarp();
+                opt = transport_solve<KC>(m, nc, A.ldc, cost, flow, su, srowdist, srowpred, ssupply, sway, deficit, lane);
+            }
+            if (lane == 0) {
+                const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+                double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
+                dist = __ddiv_rn(dist, A.pqn[q]);                 // S6(f)
+                dist = __ddiv_rn(dist, Cn);
+                dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
+                A.out[p] = dist;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace wmd

@@ -1,0 +1,671 @@
+// wmd_b200.cu -- host engine + C ABI of libwmd_b200.so (see include/wmd_b200.h).
+//
+// Pipeline per chunk of pairs (all on one CUDA stream, chunks alternate between two streams so
+// that the FP32-bound cost kernel of one chunk overlaps the latency-bound solver of the other
+// and the chunk's tiles stay L2-resident between the two):
+//     K1 nbow_pairs_kernel -> K2 cost_tiles_kernel (+ large variant) -> K3 emd_solve_kernel<KC>
+// There is no CPU implementation behind this ABI: without a device every entry fails.
+#include "../../include/wmd_b200.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "nbow.cuh"
+#include "cost.cuh"
+#include "solve.cuh"
+#include "rwmd.cuh"
+
+using namespace wmd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(WMD_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return WMD_OK;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return fail(WMD_ECUDA, "cudaFree: %s", cudaGetErrorString(e)); }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(WMD_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return WMD_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Workspace {
+    DevBuf ids1, ids2, off1, off2;              // staged inputs (host entries)
+    DevBuf rows1, cnt1, ip1, rows2, cnt2, ip2;  // per token slot
+    DevBuf u12, meta, pqn, extra, maxc;         // per pair
+    DevBuf tiles, out, status, scratch;
+    DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
+    DevBuf counters;                            // 4 x unsigned
+    void release()
+    {
+        DevBuf *all[] = { &ids1, &ids2, &off1, &off2, &rows1, &cnt1, &ip1, &rows2, &cnt2, &ip2, &u12, &meta, &pqn,
+                          &extra, &maxc, &tiles, &out, &status, &scratch, &lb, &l1, &l2, &am1, &am2, &counters };
+        for (DevBuf *b : all) b->release();
+    }
+};
+
+struct ProfRec { int kind; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct wmd_engine {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    float *table = nullptr;
+    int64_t V = 0;
+    int32_t d = 0, ld = 0;
+    int32_t *map = nullptr;
+    int64_t nmap = 0;
+    int32_t *rank = nullptr;
+    SumPlan plan;
+    cudaStream_t streams[2] = { nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr }, ev_slot[2] = { nullptr, nullptr };
+    bool slot_used[2] = { false, false };
+    Workspace ws[2];
+    unsigned long long *stats = nullptr;        // device [6]
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    double prof_ms[WMD_K_COUNT] = { 0 };
+    int64_t prof_n[WMD_K_COUNT] = { 0 };
+};
+
+namespace {
+
+void build_plan_rec(int start, int n, SumPlan &pl, bool &ok)
+{
+    if (n <= 128) {
+        if (pl.nops >= kMaxPlanOps) { ok = false; return; }
+        pl.start[pl.nops] = start; pl.len[pl.nops] = n; pl.adds[pl.nops] = 0; pl.nops++;
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    build_plan_rec(start, n2, pl, ok);
+    build_plan_rec(start + n2, n - n2, pl, ok);
+    if (ok) pl.adds[pl.nops - 1]++;
+}
+
+struct Prof {
+    wmd_engine *E; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Prof(wmd_engine *E_, int kind_, cudaStream_t st_) : E(E_), kind(kind_), st(st_)
+    {
+        if (E->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~Prof()
+    {
+        if (E->profiling) { cudaEventRecord(b, st); E->prof.push_back({ kind, a, b }); }
+    }
+};
+
+Vocab make_vocab(const wmd_engine *E)
+{
+    Vocab v;
+    v.table = E->table; v.V = E->V; v.d = E->d; v.ld = E->ld; v.map = E->map; v.nmap = E->nmap; v.rank = E->rank;
+    return v;
+}
+
+struct ChunkOut {
+    double *out; int32_t *status;           // indexed by global pair number p
+    // optional rwmd outputs
+    bool rwmd = false;
+    double *lb = nullptr, *l1 = nullptr, *l2 = nullptr;
+    int32_t *am1 = nullptr, *am2 = nullptr; // chunk-relative token offsets
+    bool solve = true;
+};
+
+// Launch K1..K3 for pairs [p0, p0 + Bc) on stream st. tok caps bound the token slots of the chunk.
+int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2,
+              int64_t p0, int32_t Bc, int64_t tokcap1, int64_t tokcap2, int32_t ml1, int32_t ml2,
+              const ChunkOut &O)
+{
+    if (Bc <= 0) return WMD_OK;
+    ml1 = std::max(ml1, 1); ml2 = std::max(ml2, 1);
+    const int ML = std::max(ml1, ml2);
+    const int64_t tile_stride = (int64_t)ml1 * ml2;
+    int rc;
+    if ((rc = W.rows1.ensure(tokcap1 * 4)) || (rc = W.cnt1.ensure(tokcap1 * 4)) || (rc = W.ip1.ensure(tokcap1 * 4)) ||
+        (rc = W.rows2.ensure(tokcap2 * 4)) || (rc = W.cnt2.ensure(tokcap2 * 4)) || (rc = W.ip2.ensure(tokcap2 * 4)) ||
+        (rc = W.u12.ensure((size_t)Bc * 4)) || (rc = W.meta.ensure((size_t)Bc * 4)) || (rc = W.pqn.ensure((size_t)Bc * 8)) ||
+        (rc = W.extra.ensure((size_t)Bc * 8)) || (rc = W.maxc.ensure((size_t)Bc * 4)) ||
+        (rc = W.tiles.ensure((size_t)Bc * tile_stride * 4)) || (rc = W.counters.ensure(64)))
+        return rc;
+
+    // ---- K1
+    PairWork pw;
+    pw.rows1 = W.rows1.as<int32_t>(); pw.cnt1 = W.cnt1.as<int32_t>(); pw.ip1 = W.ip1.as<int32_t>();
+    pw.rows2 = W.rows2.as<int32_t>(); pw.cnt2 = W.cnt2.as<int32_t>(); pw.ip2 = W.ip2.as<int32_t>();
+    pw.u12 = W.u12.as<int32_t>(); pw.meta = W.meta.as<int32_t>(); pw.pqn = W.pqn.as<double>(); pw.extra = W.extra.as<double>();
+    pw.stats = E->stats;
+    const Vocab vc = make_vocab(E);
+    {
+        const int Lp = ML;
+        const int wpb = Lp <= 64 ? 8 : 4;
+        const size_t smem = nbow_smem_per_warp(Lp) * wpb;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<int64_t>((Bc + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+        Prof pr(E, WMD_K_NBOW, st);
+        nbow_pairs_kernel<<<grid, wpb * 32, smem, st>>>(s1, s2, vc, p0, Bc, Lp, pw, O.out, O.status);
+        CK(cudaGetLastError());
+    }
+    // ---- K2
+    int tb;
+    {
+        CostArgs A;
+        A.vc = vc; A.plan = E->plan; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
+        int ldr4 = (E->d + 3) / 4;
+        if ((ldr4 & 1) == 0) ldr4++;
+        A.ldr = ldr4 * 4;
+        const size_t rowbytes = (size_t)A.ldr * 4;
+        size_t budget = 96 * 1024;
+        int rcap = (int)(budget / rowbytes);
+        if (rcap < 16) { budget = std::min<size_t>(E->smem_optin - 4096, 200 * 1024); rcap = (int)(budget / rowbytes); }
+        if (rcap < 2) return fail(WMD_EINVAL, "embedding width %d does not fit the shared-memory staging buffer", E->d);
+        rcap = std::min(rcap, 512);
+        tb = std::min(32, rcap / 2);
+        A.tb = tb; A.rcap = rcap;
+        A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
+        A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride; A.maxc = W.maxc.as<float>();
+        const size_t smem = (size_t)rcap * rowbytes;
+        CK(cudaFuncSetAttribute(cost_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count * 2);
+            Prof pr(E, WMD_K_COST, st);
+            cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
+            CK(cudaGetLastError());
+        }
+        if (ML > tb) {
+            const size_t smem_l = (size_t)2 * tb * rowbytes;
+            CK(cudaFuncSetAttribute(cost_tiles_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count * 2);
+            Prof pr(E, WMD_K_COST, st);
+            cost_tiles_large_kernel<<<grid, kCostThreads, smem_l, st>>>(A);
+            CK(cudaGetLastError());
+        }
+    }
+    // ---- K5 (optional)
+    if (O.rwmd) {
+        RwmdArgs R;
+        R.s1 = s1; R.s2 = s2; R.p0 = p0; R.npairs = Bc; R.Lp = ML;
+        R.cnt1 = pw.cnt1; R.cnt2 = pw.cnt2; R.u12 = pw.u12;
+        R.tiles = W.tiles.as<float>(); R.tile_stride = tile_stride; R.status = O.status;
+        R.lb = O.lb; R.l1 = O.l1; R.l2 = O.l2; R.argmin_rows = O.am1; R.argmin_cols = O.am2;
+        const int wpb = 8;
+        const size_t smem = (size_t)wpb * ML * 8;
+        const int grid = (int)std::min<int64_t>((Bc + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+        Prof pr(E, WMD_K_RWMD, st);
+        rwmd_pairs_kernel<<<grid, wpb * 32, smem, st>>>(R);
+        CK(cudaGetLastError());
+    }
+    if (!O.solve) return WMD_OK;
+    // ---- K3
+    CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
+    for (int cls = kClsA; cls <= kClsC; ++cls) {
+        if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
+        if (cls == kClsC && ML < 64) continue;
+        SolveArgs S;
+        S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
+        const int cap = cls == kClsA ? 32 : (cls == kClsB ? 64 : kMaxDocLen + 1);
+        S.mr = std::min(cap, ML); S.mc = std::min(cap, ML + 1);
+        S.ldc = S.mc | 1;
+        S.use_global = cls == kClsC;
+        S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
+        S.tiles = W.tiles.as<float>(); S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
+        S.counter = W.counters.as<unsigned int>() + cls;
+        S.out = O.out; S.status = O.status;
+        int wpb = 8;
+        size_t per_warp = solve_smem_per_warp(S.mr, S.mc, S.ldc, S.use_global);
+        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+        const size_t smem = per_warp * wpb;
+        int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (cls == kClsC ? 2 : 8));
+        grid = std::max(grid, 1);
+        S.scratch = nullptr;
+        if (S.use_global) {
+            if ((rc = W.scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;
+            S.scratch = W.scratch.as<int32_t>();
+        }
+        Prof pr(E, WMD_K_SOLVE, st);
+        if (cls == kClsA) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_kernel<1><<<grid, wpb * 32, smem, st>>>(S);
+        } else if (cls == kClsB) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_kernel<2><<<grid, wpb * 32, smem, st>>>(S);
+        } else {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_kernel<9><<<grid, wpb * 32, smem, st>>>(S);
+        }
+        CK(cudaGetLastError());
+    }
+    return WMD_OK;
+}
+
+int64_t chunk_pairs(int ml1, int ml2)
+{
+    const int64_t tile = (int64_t)std::max(ml1, 1) * std::max(ml2, 1) * 4;
+    int64_t c = (int64_t)(768ll << 20) / tile;
+    c = std::min<int64_t>(c, 65536);
+    return std::max<int64_t>(c, 256);
+}
+
+int scan_offsets(const int64_t *off, int64_t n, int32_t &maxlen, const char *name)
+{
+    int64_t m = 0;
+    for (int64_t p = 0; p < n; ++p) {
+        const int64_t l = off[p + 1] - off[p];
+        if (l < 0) return fail(WMD_EINVAL, "%s offsets are not monotone at %lld", name, (long long)p);
+        m = std::max(m, l);
+    }
+    if (m > WMD_MAX_DOC_LEN) return fail(WMD_EINVAL, "%s holds a document of %lld tokens; the limit is %d", name, (long long)m, WMD_MAX_DOC_LEN);
+    maxlen = (int32_t)m;
+    return WMD_OK;
+}
+
+int set_device(wmd_engine *E)
+{
+    CK(cudaSetDevice(E->device));
+    return WMD_OK;
+}
+
+int reset_stats(wmd_engine *E, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(E->stats, 0, 6 * sizeof(unsigned long long), st));
+    return WMD_OK;
+}
+
+// shared body of the host entries: chunked H2D -> kernels -> D2H on the two internal streams
+struct HostJob {
+    const int32_t *ids1; const int64_t *off1; const int32_t *ids2; const int64_t *off2; int64_t npairs;
+    double *out; int32_t *status;
+    bool rwmd = false, solve = true;
+    double *lb = nullptr, *l1 = nullptr, *l2 = nullptr; int32_t *am1 = nullptr, *am2 = nullptr;
+};
+
+int run_host_job(wmd_engine *E, const HostJob &J)
+{
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if (J.npairs < 0 || (J.npairs > 0 && (!J.off1 || !J.off2))) return fail(WMD_EINVAL, "null offsets");
+    if (J.npairs == 0) return WMD_OK;
+    int32_t ml1, ml2;
+    if ((rc = scan_offsets(J.off1, J.npairs, ml1, "side 1"))) return rc;
+    if ((rc = scan_offsets(J.off2, J.npairs, ml2, "side 2"))) return rc;
+    if ((J.off1[J.npairs] > J.off1[0] && !J.ids1) || (J.off2[J.npairs] > J.off2[0] && !J.ids2)) return fail(WMD_EINVAL, "null ids");
+    if ((rc = reset_stats(E, E->streams[0]))) return rc;
+    CK(cudaEventRecord(E->ev_fork, E->streams[0]));
+    CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
+    const int64_t CH = chunk_pairs(ml1, ml2);
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < J.npairs; c0 += CH, slot ^= 1) {
+        const int32_t Bc = (int32_t)std::min<int64_t>(CH, J.npairs - c0);
+        Workspace &W = E->ws[slot];
+        cudaStream_t st = E->streams[slot];
+        const int64_t t1 = J.off1[c0 + Bc] - J.off1[c0], t2 = J.off2[c0 + Bc] - J.off2[c0];
+        if ((rc = W.ids1.ensure((size_t)std::max<int64_t>(t1, 1) * 4)) || (rc = W.ids2.ensure((size_t)std::max<int64_t>(t2, 1) * 4)) ||
+            (rc = W.off1.ensure((size_t)(Bc + 1) * 8)) || (rc = W.off2.ensure((size_t)(Bc + 1) * 8)) ||
+            (rc = W.out.ensure((size_t)Bc * 8)) || (rc = W.status.ensure((size_t)Bc * 4)))
+            return rc;
+        if (t1) CK(cudaMemcpyAsync(W.ids1.p, J.ids1 + J.off1[c0], (size_t)t1 * 4, cudaMemcpyHostToDevice, st));
+        if (t2) CK(cudaMemcpyAsync(W.ids2.p, J.ids2 + J.off2[c0], (size_t)t2 * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(W.off1.p, J.off1 + c0, (size_t)(Bc + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(W.off2.p, J.off2 + c0, (size_t)(Bc + 1) * 8, cudaMemcpyHostToDevice, st));
+        DocSide s1{}, s2{};
+        s1.ids = W.ids1.as<int32_t>() - J.off1[c0]; s1.off = W.off1.as<int64_t>();
+        s2.ids = W.ids2.as<int32_t>() - J.off2[c0]; s2.off = W.off2.as<int64_t>();
+        ChunkOut O;
+        O.out = W.out.as<double>(); O.status = W.status.as<int32_t>(); O.solve = J.solve; O.rwmd = J.rwmd;
+        if (J.rwmd) {
+            if ((rc = W.lb.ensure((size_t)Bc * 8)) || (rc = W.l1.ensure((size_t)Bc * 8)) || (rc = W.l2.ensure((size_t)Bc * 8)) ||
+                (rc = W.am1.ensure((size_t)std::max<int64_t>(t1, 1) * 4)) || (rc = W.am2.ensure((size_t)std::max<int64_t>(t2, 1) * 4)))
+                return rc;
+            O.lb = W.lb.as<double>(); O.l1 = W.l1.as<double>(); O.l2 = W.l2.as<double>();
+            O.am1 = J.am1 ? W.am1.as<int32_t>() : nullptr; O.am2 = J.am2 ? W.am2.as<int32_t>() : nullptr;
+            if (O.am1) CK(cudaMemsetAsync(W.am1.p, 0xff, (size_t)std::max<int64_t>(t1, 1) * 4, st));
+            if (O.am2) CK(cudaMemsetAsync(W.am2.p, 0xff, (size_t)std::max<int64_t>(t2, 1) * 4, st));
+        }
+        if ((rc = run_chunk(E, W, st, s1, s2, 0, Bc, std::max<int64_t>(t1, 1), std::max<int64_t>(t2, 1), ml1, ml2, O))) return rc;
+        if (J.out) CK(cudaMemcpyAsync(J.out + c0, W.out.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
+        if (J.status) CK(cudaMemcpyAsync(J.status + c0, W.status.p, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+        if (J.rwmd) {
+            if (J.lb) CK(cudaMemcpyAsync(J.lb + c0, W.lb.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
+            if (J.l1) CK(cudaMemcpyAsync(J.l1 + c0, W.l1.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
+            if (J.l2) CK(cudaMemcpyAsync(J.l2 + c0, W.l2.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
+            if (J.am1 && t1) CK(cudaMemcpyAsync(J.am1 + J.off1[c0], W.am1.p, (size_t)t1 * 4, cudaMemcpyDeviceToHost, st));
+            if (J.am2 && t2) CK(cudaMemcpyAsync(J.am2 + J.off2[c0], W.am2.p, (size_t)t2 * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(E->ev_slot[slot], st));
+        E->slot_used[slot] = true;
+    }
+    CK(cudaStreamSynchronize(E->streams[0]));
+    CK(cudaStreamSynchronize(E->streams[1]));
+    E->slot_used[0] = E->slot_used[1] = false;
+    return WMD_OK;
+}
+
+// shared body of the device entries: fork from the caller's stream, chunk, join back; no host sync
+int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t total1, int64_t total2,
+                int32_t ml1, int32_t ml2, int64_t npairs, double *out, int32_t *status, cudaStream_t us)
+{
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if (npairs < 0 || !out) return fail(WMD_EINVAL, "bad arguments");
+    if (npairs == 0) return WMD_OK;
+    if (ml1 < 0 || ml2 < 0 || ml1 > WMD_MAX_DOC_LEN || ml2 > WMD_MAX_DOC_LEN)
+        return fail(WMD_EINVAL, "max_len must be within [0, %d]", WMD_MAX_DOC_LEN);
+    ml1 = std::max(ml1, 1); ml2 = std::max(ml2, 1);
+    CK(cudaEventRecord(E->ev_fork, us));
+    CK(cudaStreamWaitEvent(E->streams[0], E->ev_fork, 0));
+    CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
+    if ((rc = reset_stats(E, E->streams[0]))) return rc;
+    CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
+    CK(cudaStreamWaitEvent(E->streams[1], E->ev_join[0], 0));        // stats reset precedes both streams' kernels
+    const int64_t CH = chunk_pairs(ml1, ml2);
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot ^= 1) {
+        const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - c0);
+        Workspace &W = E->ws[slot];
+        if (!status) { if ((rc = W.status.ensure((size_t)Bc * 4))) return rc; }
+        ChunkOut O;
+        O.out = out; O.status = status;
+        int64_t p0 = c0;
+        DocSide a = s1, b = s2;
+        if (!status) {
+            // scratch status indexed from 0: shift so that status[p0 + q] lands in the scratch buffer
+            O.status = W.status.as<int32_t>() - c0;
+        }
+        const int64_t cap1 = std::max<int64_t>(1, std::min<int64_t>(total1, (int64_t)Bc * ml1));
+        const int64_t cap2 = std::max<int64_t>(1, std::min<int64_t>(total2, (int64_t)Bc * ml2));
+        if ((rc = run_chunk(E, W, E->streams[slot], a, b, p0, Bc, cap1, cap2, ml1, ml2, O))) return rc;
+    }
+    CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
+    CK(cudaEventRecord(E->ev_join[1], E->streams[1]));
+    CK(cudaStreamWaitEvent(us, E->ev_join[0], 0));
+    CK(cudaStreamWaitEvent(us, E->ev_join[1], 0));
+    return WMD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wmd_last_error(void) { return g_err.c_str(); }
+const char *wmd_version(void) { return "wmd_b200 0.1 (sm_100a)"; }
+
+int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride, int32_t normalize,
+               int32_t device, wmd_handle *out)
+{
+    if (!out) return fail(WMD_EINVAL, "out is null");
+    *out = nullptr;
+    if (!table_host || V <= 0 || d <= 0 || row_stride < d) return fail(WMD_EINVAL, "bad table arguments");
+    if (V > 0x7fffffff) return fail(WMD_EINVAL, "V too large");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(WMD_ENODEV, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(WMD_ENODEV, "device %d out of range (have %d)", device, ndev);
+    wmd_engine *E = new wmd_engine();
+    E->device = device;
+    int rc = WMD_OK;
+    auto bail = [&](int code) { wmd_destroy(E); return code; };
+    if ((rc = set_device(E))) return bail(rc);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(WMD_ECUDA, "cudaGetDeviceProperties failed"));
+    E->sm_count = prop.multiProcessorCount;
+    E->smem_optin = prop.sharedMemPerBlockOptin;
+    E->V = V; E->d = d; E->ld = (d + 3) & ~3;
+    E->plan.nops = 0;
+    bool ok = true;
+    build_plan_rec(0, d, E->plan, ok);
+    if (!ok) return bail(fail(WMD_EINVAL, "embedding width %d too large", d));
+    if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
+    if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));
+    if (cudaMemcpy2D(E->table, (size_t)E->ld * 4, table_host, (size_t)row_stride * 4, (size_t)d * 4, (size_t)V, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(WMD_ECUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    for (int i = 0; i < 2; ++i) {
+        if (cudaStreamCreateWithFlags(&E->streams[i], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(WMD_ECUDA, "stream create failed"));
+        if (cudaEventCreateWithFlags(&E->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(WMD_ECUDA, "event create failed"));
+        if (cudaEventCreateWithFlags(&E->ev_slot[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(WMD_ECUDA, "event create failed"));
+    }
+    if (cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(WMD_ECUDA, "event create failed"));
+    if (cudaMalloc(&E->stats, 6 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc failed"));
+    cudaMemset(E->stats, 0, 6 * sizeof(unsigned long long));
+    if (normalize) {
+        normalize_rows_kernel<<<(unsigned)((V + 127) / 128), 128>>>(E->table, V, d, E->ld, E->plan);
+        if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(WMD_ECUDA, "normalize failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    *out = E;
+    return WMD_OK;
+}
+
+int wmd_destroy(wmd_handle E)
+{
+    if (!E) return WMD_OK;
+    cudaSetDevice(E->device);
+    cudaDeviceSynchronize();
+    for (auto &r : E->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (int i = 0; i < 2; ++i) {
+        E->ws[i].release();
+        if (E->streams[i]) cudaStreamDestroy(E->streams[i]);
+        if (E->ev_join[i]) cudaEventDestroy(E->ev_join[i]);
+        if (E->ev_slot[i]) cudaEventDestroy(E->ev_slot[i]);
+    }
+    if (E->ev_fork) cudaEventDestroy(E->ev_fork);
+    if (E->table) cudaFree(E->table);
+    if (E->map) cudaFree(E->map);
+    if (E->rank) cudaFree(E->rank);
+    if (E->stats) cudaFree(E->stats);
+    delete E;
+    return WMD_OK;
+}
+
+int wmd_set_token_map(wmd_handle E, const int32_t *id_to_row_host, int64_t n)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    CK(cudaDeviceSynchronize());
+    if (E->map) { CK(cudaFree(E->map)); E->map = nullptr; E->nmap = 0; }
+    if (!id_to_row_host || n <= 0) return WMD_OK;
+    CK(cudaMalloc(&E->map, (size_t)n * 4));
+    CK(cudaMemcpy(E->map, id_to_row_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+    E->nmap = n;
+    return WMD_OK;
+}
+
+int wmd_set_rank(wmd_handle E, const int32_t *rank_host, int64_t V)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    CK(cudaDeviceSynchronize());
+    if (E->rank) { CK(cudaFree(E->rank)); E->rank = nullptr; }
+    if (!rank_host) return WMD_OK;
+    if (V != E->V) return fail(WMD_EINVAL, "rank table has %lld entries, the embedding table %lld rows", (long long)V, (long long)E->V);
+    std::vector<char> seen((size_t)V, 0);
+    for (int64_t i = 0; i < V; ++i) {
+        const int32_t r = rank_host[i];
+        if (r < 0 || r >= V || seen[(size_t)r]) return fail(WMD_EINVAL, "rank table is not a permutation of 0..V-1 (entry %lld)", (long long)i);
+        seen[(size_t)r] = 1;
+    }
+    CK(cudaMalloc(&E->rank, (size_t)V * 4));
+    CK(cudaMemcpy(E->rank, rank_host, (size_t)V * 4, cudaMemcpyHostToDevice));
+    return WMD_OK;
+}
+
+int wmd_get_table(wmd_handle E, float *out_host)
+{
+    if (!E || !out_host) return fail(WMD_EINVAL, "null argument");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy2D(out_host, (size_t)E->d * 4, E->table, (size_t)E->ld * 4, (size_t)E->d * 4, (size_t)E->V, cudaMemcpyDeviceToHost));
+    return WMD_OK;
+}
+
+int wmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, const int32_t *ids2, const int64_t *off2,
+                   int64_t npairs, int32_t mode, double *out, int32_t *status)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (!out && npairs > 0) return fail(WMD_EINVAL, "out is null");
+    HostJob J{ ids1, off1, ids2, off2, npairs, out, status };
+    return run_host_job(E, J);
+}
+
+int wmd_rwmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, const int32_t *ids2, const int64_t *off2,
+                        int64_t npairs, double *lb, double *l1, double *l2, int32_t *argmin_rows, int32_t *argmin_cols,
+                        int32_t *status)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (!lb && npairs > 0) return fail(WMD_EINVAL, "lb is null");
+    HostJob J{ ids1, off1, ids2, off2, npairs, nullptr, status };
+    J.rwmd = true; J.solve = false; J.lb = lb; J.l1 = l1; J.l2 = l2; J.am1 = argmin_rows; J.am2 = argmin_cols;
+    return run_host_job(E, J);
+}
+
+int wmd_pairs_dev(wmd_handle E, const int32_t *ids1, const int64_t *off1, int64_t total1, int32_t max_len1,
+                  const int32_t *ids2, const int64_t *off2, int64_t total2, int32_t max_len2,
+                  int64_t npairs, int32_t mode, double *out, int32_t *status, void *stream)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (npairs > 0 && (!off1 || !off2)) return fail(WMD_EINVAL, "null offsets");
+    DocSide s1{}, s2{};
+    s1.ids = ids1; s1.off = off1; s2.ids = ids2; s2.off = off2;
+    return run_dev_job(E, s1, s2, total1, total2, max_len1, max_len2, npairs, out, status, (cudaStream_t)stream);
+}
+
+int wmd_pairs_padded_dev(wmd_handle E, const int32_t *a, int32_t L1, const int32_t *b, int32_t L2, int64_t npairs,
+                         int32_t pad_id, int32_t mode, double *out, int32_t *status, void *stream)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (npairs > 0 && (!a || !b)) return fail(WMD_EINVAL, "null ids");
+    if (L1 <= 0 || L2 <= 0) return fail(WMD_EINVAL, "padded lengths must be positive");
+    DocSide s1{}, s2{};
+    s1.ids = a; s1.off = nullptr; s1.L = L1; s1.pad_id = pad_id; s1.has_pad = 1;
+    s2.ids = b; s2.off = nullptr; s2.L = L2; s2.pad_id = pad_id; s2.has_pad = 1;
+    return run_dev_job(E, s1, s2, npairs * L1, npairs * L2, L1, L2, npairs, out, status, (cudaStream_t)stream);
+}
+
+int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t ndocs,
+                  int32_t *rows, int32_t *counts, double *weights, int32_t *uniq)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (ndocs < 0 || (ndocs > 0 && (!off || !rows || !counts || !weights || !uniq))) return fail(WMD_EINVAL, "null argument");
+    if (ndocs == 0) return WMD_OK;
+    if (ndocs > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    int32_t ml;
+    if ((rc = scan_offsets(off, ndocs, ml, "documents"))) return rc;
+    const int64_t base = off[0], total = off[ndocs] - base;
+    if (total > 0 && !ids) return fail(WMD_EINVAL, "null ids");
+    Workspace &W = E->ws[0];
+    cudaStream_t st = E->streams[0];
+    const size_t tb = (size_t)std::max<int64_t>(total, 1);
+    if ((rc = W.ids1.ensure(tb * 4)) || (rc = W.off1.ensure((size_t)(ndocs + 1) * 8)) || (rc = W.rows1.ensure(tb * 4)) ||
+        (rc = W.cnt1.ensure(tb * 4)) || (rc = W.pqn.ensure(tb * 8)) || (rc = W.u12.ensure((size_t)ndocs * 4)))
+        return rc;
+    if (total) CK(cudaMemcpyAsync(W.ids1.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(W.off1.p, off, (size_t)(ndocs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(W.rows1.p, 0xff, tb * 4, st));
+    CK(cudaMemsetAsync(W.cnt1.p, 0, tb * 4, st));
+    CK(cudaMemsetAsync(W.pqn.p, 0, tb * 8, st));
+    DocSide s{};
+    s.ids = W.ids1.as<int32_t>() - base; s.off = W.off1.as<int64_t>();
+    const int Lp = std::max(ml, 1);
+    const int wpb = Lp <= 64 ? 8 : 4;
+    const size_t smem = nbow_smem_per_warp(Lp) * wpb;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_docs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((ndocs + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+    {
+        Prof pr(E, WMD_K_NBOW, st);
+        nbow_docs_kernel<<<grid, wpb * 32, smem, st>>>(s, make_vocab(E), (int32_t)ndocs, Lp,
+                                                      W.rows1.as<int32_t>() - base, W.cnt1.as<int32_t>() - base,
+                                                      W.pqn.as<double>() - base, W.u12.as<int32_t>());
+        CK(cudaGetLastError());
+    }
+    if (total) {
+        CK(cudaMemcpyAsync(rows + base, W.rows1.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(counts + base, W.cnt1.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(weights + base, W.pqn.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(uniq, W.u12.p, (size_t)ndocs * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return WMD_OK;
+}
+
+int wmd_set_profiling(wmd_handle E, int32_t enabled)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    E->profiling = enabled != 0;
+    return WMD_OK;
+}
+
+int wmd_get_profile(wmd_handle E, double *ms, int64_t *launches, int32_t reset)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    CK(cudaDeviceSynchronize());
+    for (auto &r : E->prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { E->prof_ms[r.kind] += t; E->prof_n[r.kind] += 1; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    E->prof.clear();
+    for (int k = 0; k < WMD_K_COUNT; ++k) {
+        if (ms) ms[k] = E->prof_ms[k];
+        if (launches) launches[k] = E->prof_n[k];
+        if (reset) { E->prof_ms[k] = 0; E->prof_n[k] = 0; }
+    }
+    return WMD_OK;
+}
+
+int wmd_get_last_stats(wmd_handle E, int64_t *values)
+{
+    if (!E || !values) return fail(WMD_EINVAL, "null argument");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[6];
+    CK(cudaMemcpy(h, E->stats, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) values[i] = (int64_t)h[i];
+    return WMD_OK;
+}
+
+}  // extern "C"

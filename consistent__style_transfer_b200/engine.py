@@ -1,0 +1,203 @@
+"""WMDEngine: thin Python owner of a ``wmd_handle`` (include/wmd_b200.h).
+
+numpy arrays go through the ``*_host`` entries (the library does its own chunked copies);
+torch CUDA tensors go through the ``*_dev`` entries on the current torch stream with no host
+synchronisation.  Nothing here computes: every number comes out of libwmd_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_f32p, c_f64p, c_i32p, c_i64p
+
+KERNEL_KINDS = ("nbow", "cost", "solve", "rwmd", "misc")
+MODE_PYEMD = 0
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a: Optional[np.ndarray], ct):
+    return None if a is None else a.ctypes.data_as(ct)
+
+
+def docs_to_csr(docs: Sequence[Sequence[int]]):
+    """list of id lists -> (ids int32, off int64)"""
+    lens = np.fromiter((len(d) for d in docs), dtype=np.int64, count=len(docs))
+    off = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    ids = np.fromiter((t for d in docs for t in d), dtype=np.int32, count=int(off[-1]))
+    return ids, off
+
+
+class WMDEngine:
+    """One handle = one device copy of the embedding table + maps + workspace."""
+
+    def __init__(self, vectors: np.ndarray, normalize: bool = False, device: int = 0,
+                 rank: Optional[np.ndarray] = None, token_map: Optional[np.ndarray] = None):
+        self._L = _lib.load()
+        vectors = np.asarray(vectors)
+        if vectors.ndim != 2:
+            raise ValueError("vectors must be [V, d]")
+        v = _np(vectors, np.float32)
+        self.V, self.d = int(v.shape[0]), int(v.shape[1])
+        self.device = int(device)
+        h = _lib.c_handle()
+        _lib.check(self._L.wmd_create(_ptr(v, c_f32p), self.V, self.d, self.d, int(bool(normalize)), self.device,
+                                      ctypes.byref(h)))
+        self._h = h
+        if rank is not None:
+            self.set_rank(rank)
+        if token_map is not None:
+            self.set_token_map(token_map)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.wmd_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise RuntimeError("WMDEngine is closed")
+        return self._h
+
+    # -- configuration ----------------------------------------------------------------------
+    def set_token_map(self, id_to_row: Optional[np.ndarray]):
+        if id_to_row is None:
+            _lib.check(self._L.wmd_set_token_map(self._handle(), None, 0))
+            return
+        m = _np(id_to_row, np.int32)
+        _lib.check(self._L.wmd_set_token_map(self._handle(), _ptr(m, c_i32p), m.shape[0]))
+
+    def set_rank(self, rank: Optional[np.ndarray]):
+        if rank is None:
+            _lib.check(self._L.wmd_set_rank(self._handle(), None, 0))
+            return
+        r = _np(rank, np.int32)
+        _lib.check(self._L.wmd_set_rank(self._handle(), _ptr(r, c_i32p), r.shape[0]))
+
+    def table(self) -> np.ndarray:
+        out = np.empty((self.V, self.d), np.float32)
+        _lib.check(self._L.wmd_get_table(self._handle(), _ptr(out, c_f32p)))
+        return out
+
+    # -- scoring: host buffers --------------------------------------------------------------
+    def wmd_pairs(self, ids1, off1, ids2, off2, out: Optional[np.ndarray] = None,
+                  status: Optional[np.ndarray] = None):
+        """WMD of CSR-packed pairs held in host memory. Returns (float64[B], int32 status[B])."""
+        ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
+        off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
+        B = off1.shape[0] - 1
+        if off2.shape[0] - 1 != B:
+            raise ValueError("both sides must hold the same number of documents")
+        if out is None:
+            out = np.empty(B, np.float64)
+        if status is None:
+            status = np.empty(B, np.int32)
+        _lib.check(self._L.wmd_pairs_host(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p),
+                                          _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B, MODE_PYEMD,
+                                          _ptr(out, c_f64p), _ptr(status, c_i32p)))
+        return out, status
+
+    def wmd_pairs_ptr(self, ids1_ptr: int, off1_ptr: int, ids2_ptr: int, off2_ptr: int, npairs: int,
+                      out_ptr: int, status_ptr: int = 0):
+        """Raw host-pointer form (pinned torch tensors' data_ptr()): no numpy wrapping, no copies."""
+        f = self._L.wmd_pairs_host
+        _lib.check(f(self._handle(), ctypes.cast(ids1_ptr, c_i32p), ctypes.cast(off1_ptr, c_i64p),
+                     ctypes.cast(ids2_ptr, c_i32p), ctypes.cast(off2_ptr, c_i64p), int(npairs), MODE_PYEMD,
+                     ctypes.cast(out_ptr, c_f64p), ctypes.cast(status_ptr, c_i32p) if status_ptr else None))
+
+    def nbow(self, ids, off):
+        """Per document: (rows int32, counts int32, weights float64) slices of length uniq[p] at off[p]."""
+        ids, off = _np(ids, np.int32), _np(off, np.int64)
+        n = off.shape[0] - 1
+        rows = np.full(ids.shape[0], -1, np.int32)
+        counts = np.zeros(ids.shape[0], np.int32)
+        weights = np.zeros(ids.shape[0], np.float64)
+        uniq = np.zeros(n, np.int32)
+        _lib.check(self._L.wmd_nbow_host(self._handle(), _ptr(ids, c_i32p), _ptr(off, c_i64p), n,
+                                         _ptr(rows, c_i32p), _ptr(counts, c_i32p), _ptr(weights, c_f64p),
+                                         _ptr(uniq, c_i32p)))
+        return rows, counts, weights, uniq
+
+    def rwmd_pairs(self, ids1, off1, ids2, off2, want_argmin: bool = True):
+        """Relaxed WMD lower bound. Returns dict(lb, l1, l2, argmin_rows, argmin_cols, status)."""
+        ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
+        off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
+        B = off1.shape[0] - 1
+        lb = np.empty(B, np.float64); l1 = np.empty(B, np.float64); l2 = np.empty(B, np.float64)
+        st = np.empty(B, np.int32)
+        am1 = np.full(ids1.shape[0], -1, np.int32) if want_argmin else None
+        am2 = np.full(ids2.shape[0], -1, np.int32) if want_argmin else None
+        _lib.check(self._L.wmd_rwmd_pairs_host(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p),
+                                               _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B,
+                                               _ptr(lb, c_f64p), _ptr(l1, c_f64p), _ptr(l2, c_f64p),
+                                               _ptr(am1, c_i32p), _ptr(am2, c_i32p), _ptr(st, c_i32p)))
+        return dict(lb=lb, l1=l1, l2=l2, argmin_rows=am1, argmin_cols=am2, status=st)
+
+    # -- scoring: device tensors (torch) ----------------------------------------------------
+    def wmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, out=None, status=None):
+        """CSR pairs in torch CUDA tensors (int32 ids, int64 offsets) -> float64 CUDA tensor.
+        Stream-ordered on torch's current stream; no host synchronisation."""
+        import torch
+        for t, dt in ((ids1, torch.int32), (ids2, torch.int32), (off1, torch.int64), (off2, torch.int64)):
+            if not (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.device.index == self.device):
+                raise ValueError("expected contiguous CUDA tensors (int32 ids, int64 offsets) on the engine's device")
+        B = off1.numel() - 1
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=ids1.device)
+        if status is None:
+            status = torch.empty(B, dtype=torch.int32, device=ids1.device)
+        stream = torch.cuda.current_stream(ids1.device).cuda_stream
+        _lib.check(self._L.wmd_pairs_dev(self._handle(), ids1.data_ptr(), off1.data_ptr(), ids1.numel(), int(max_len1),
+                                         ids2.data_ptr(), off2.data_ptr(), ids2.numel(), int(max_len2),
+                                         B, MODE_PYEMD, out.data_ptr(), status.data_ptr(), stream))
+        return out, status
+
+    def wmd_pairs_padded(self, a, b, pad_id: int = 0, out=None, status=None):
+        """Padded [B, L] torch CUDA id tensors (int32 or int64; pad_id skipped) -> float64[B] on device."""
+        import torch
+        if a.dtype != torch.int32:
+            a = a.to(torch.int32)
+        if b.dtype != torch.int32:
+            b = b.to(torch.int32)
+        a, b = a.contiguous(), b.contiguous()
+        if not (a.is_cuda and b.is_cuda and a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0]):
+            raise ValueError("expected two [B, L] CUDA tensors")
+        B = a.shape[0]
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=a.device)
+        if status is None:
+            status = torch.empty(B, dtype=torch.int32, device=a.device)
+        stream = torch.cuda.current_stream(a.device).cuda_stream
+        _lib.check(self._L.wmd_pairs_padded_dev(self._handle(), a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1],
+                                                B, int(pad_id), MODE_PYEMD, out.data_ptr(), status.data_ptr(), stream))
+        return out, status
+
+    # -- instrumentation --------------------------------------------------------------------
+    def set_profiling(self, enabled: bool):
+        _lib.check(self._L.wmd_set_profiling(self._handle(), int(bool(enabled))))
+
+    def profile(self, reset: bool = True):
+        ms = (ctypes.c_double * len(KERNEL_KINDS))()
+        n = (ctypes.c_int64 * len(KERNEL_KINDS))()
+        _lib.check(self._L.wmd_get_profile(self._handle(), ms, n, int(reset)))
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(KERNEL_KINDS)}
+
+    def last_stats(self):
+        v = (ctypes.c_int64 * 6)()
+        _lib.check(self._L.wmd_get_last_stats(self._handle(), v))
+        keys = ("tokens", "uniques", "cells", "solved_pairs", "max_rows", "max_cols")
+        return {k: int(v[i]) for i, k in enumerate(keys)}

@@ -1,0 +1,138 @@
+/*
+ * wmd_b200.h -- C ABI of libwmd_b200.so, the B200 (sm_100a) Word Mover's Distance engine.
+ *
+ * This is the drop-in boundary for the content-preservation scoring path of
+ * iptmt/consistent__style_transfer.  The reference has no FFI of its own on this path (it is
+ * Python calling gensim -> pyemd); each entry point below names the reference call it stands
+ * behind.  Paths are relative to /root/reference.
+ *
+ *   reference call                                              entry point here
+ *   ---------------------------------------------------------  --------------------------------
+ *   WMDdistance.load / init_sims(replace=True)                   wmd_create (+ wmd_normalize_rows)
+ *     src/wmd.py:50-55, evaluate/auto/content_preserve.py:38-41
+ *   tokenizer.ids_to_tokens + gensim OOV filter                  wmd_set_token_map, wmd_set_rank
+ *     src/vocab.py:26-27, src/wmd.py:40
+ *   WMDdistance.cal_wmd_label (the per-batch python loop)        wmd_pairs_host / wmd_pairs_dev
+ *     src/wmd.py:34-45  (caller: src/loader.py:60)
+ *   WMDdistance.cal_wmd -> wv.wmdistance -> pyemd.emd            one pair of the above
+ *     src/wmd.py:31-32
+ *   calculate_wmd_scores (per-pair loop)                         wmd_pairs_host
+ *     evaluate/auto/content_preserve.py:43-50 (caller: evaluate/eval.py:42)
+ *   gensim nbow() / Dictionary.doc2bow  [third party]            wmd_nbow_host
+ *   (not in the reference: Kusner et al. 2015 lower bound)       wmd_rwmd_pairs_host
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative WMD_E* code on failure; the message
+ *     is available from wmd_last_error() (thread-local).  Nothing throws.
+ *   - "documents" are CSR-packed int32 id lists: ids[off[p] .. off[p+1]) is document p,
+ *     off has npairs+1 int64 entries.  ids are embedding-table rows, or tokenizer ids when a
+ *     token map is installed; anything that does not map to a row in [0, V) is out of
+ *     vocabulary and is dropped (gensim's `token in self.vocab` filter).
+ *   - *_host entries take HOST pointers (pinned or pageable) and do their own chunked
+ *     host<->device copies; *_dev entries take DEVICE pointers and are ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream) with no host sync.
+ *   - the caller owns every buffer; the handle owns its device copy of the table, the maps
+ *     and a grow-only workspace.  A handle is bound to one device and is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device wmd_create fails with WMD_ENODEV.
+ *
+ * Per-pair status codes (gensim's early-outs):
+ *   0 = ok, finite distance                      1 = +inf, a document is empty after OOV removal
+ *   2 = 0.0, the union vocabulary has one token   3 = +inf, all-zero distance matrix
+ */
+#ifndef WMD_B200_H
+#define WMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wmd_engine *wmd_handle;
+
+#define WMD_OK        0
+#define WMD_EINVAL   -1   /* bad argument (null pointer, negative size, document longer than WMD_MAX_DOC_LEN, ...) */
+#define WMD_ENODEV   -2   /* no usable CUDA device */
+#define WMD_ECUDA    -3   /* a CUDA runtime call failed; see wmd_last_error() */
+#define WMD_ENOMEM   -4
+
+#define WMD_MAX_DOC_LEN 256      /* tokens per document (before OOV removal) */
+
+/* distance definition */
+#define WMD_MODE_PYEMD 0   /* pyemd emd_hat_gd_metric: 1e6-grid integer optimum (bit-faithful to the reference) */
+
+/* lifetime ------------------------------------------------------------------------------------ */
+
+/* Copies the [V, d] float32 table (HOST pointer, row_stride floats between rows) to `device`.
+ * normalize != 0 applies gensim init_sims(replace=True) on the device: each row divided by
+ * sqrt(sum(row**2)) in float32 with numpy's summation order.  */
+int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride,
+               int32_t normalize, int32_t device, wmd_handle *out);
+int wmd_destroy(wmd_handle h);
+const char *wmd_last_error(void);
+const char *wmd_version(void);
+
+/* tokenizer id -> table row (-1 = OOV), n entries; NULL/0 removes the map (ids are rows). */
+int wmd_set_token_map(wmd_handle h, const int32_t *id_to_row_host, int64_t n);
+/* rank[row] = position of the row's token in gensim Dictionary (python string sort) order.
+ * Fixes the canonical order of nBOW outputs and of the FP64 mass summation. NULL = row order. */
+int wmd_set_rank(wmd_handle h, const int32_t *rank_host, int64_t V);
+/* copy the (possibly normalised) device table back to the host, [V, d] dense */
+int wmd_get_table(wmd_handle h, float *out_host);
+
+/* scoring ------------------------------------------------------------------------------------- */
+
+/* WMD of npairs document pairs. out[npairs] float64, status[npairs] int32 (may be NULL). */
+int wmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
+                   const int32_t *ids2, const int64_t *off2, int64_t npairs,
+                   int32_t mode, double *out, int32_t *status);
+
+/* Same on device buffers, stream-ordered.  max_len1/max_len2 bound the document lengths of
+ * each side (needed to size the launch without a host sync); total1/total2 are off1[npairs],
+ * off2[npairs].  */
+int wmd_pairs_dev(wmd_handle h, const int32_t *ids1, const int64_t *off1, int64_t total1, int32_t max_len1,
+                  const int32_t *ids2, const int64_t *off2, int64_t total2, int32_t max_len2,
+                  int64_t npairs, int32_t mode, double *out, int32_t *status, void *stream);
+
+/* Padded [npairs, L1] / [npairs, L2] int32 id matrices on the device (pad_id entries are
+ * skipped wherever they occur), stream-ordered, no host sync.  For a validation hook on
+ * src/main_optimize.py:127-141 (tokens = sample_p.argmax(-1), x padded with PAD_ID=0). */
+int wmd_pairs_padded_dev(wmd_handle h, const int32_t *a, int32_t L1, const int32_t *b, int32_t L2,
+                         int64_t npairs, int32_t pad_id, int32_t mode,
+                         double *out, int32_t *status, void *stream);
+
+/* nBOW of ndocs documents: unique in-vocabulary rows in canonical order, int32 counts and
+ * FP64 weights count/len, written at the document's own CSR offset (first u entries of its
+ * slot); uniq[ndocs] receives u. */
+int wmd_nbow_host(wmd_handle h, const int32_t *ids, const int64_t *off, int64_t ndocs,
+                  int32_t *rows, int32_t *counts, double *weights, int32_t *uniq);
+
+/* Relaxed WMD lower bound per pair: lb = max(l1, l2), l1 = sum_i w1[i] min_j c[i][j] (FP64,
+ * canonical order), with the argmin column of every doc1 row / argmin row of every doc2
+ * column (lowest index on ties) written at the documents' CSR offsets.  l1/l2/argmins may be NULL. */
+int wmd_rwmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
+                        const int32_t *ids2, const int64_t *off2, int64_t npairs,
+                        double *lb, double *l1, double *l2,
+                        int32_t *argmin_rows, int32_t *argmin_cols, int32_t *status);
+
+/* instrumentation ----------------------------------------------------------------------------- */
+
+/* When enabled, every kernel launch is bracketed by CUDA events on its own stream. */
+int wmd_set_profiling(wmd_handle h, int32_t enabled);
+#define WMD_K_NBOW   0
+#define WMD_K_COST   1
+#define WMD_K_SOLVE  2
+#define WMD_K_RWMD   3
+#define WMD_K_MISC   4
+#define WMD_K_COUNT  5
+/* accumulated since the last reset: ms[k] device milliseconds, launches[k] launch count */
+int wmd_get_profile(wmd_handle h, double *ms, int64_t *launches, int32_t reset);
+/* totals of the last wmd_pairs_* call: sum over pairs of tokens, unique rows and tile cells
+ * (for the algorithmic-bytes figure of the roofline). values[0..5] =
+ * {tokens1+tokens2, uniq1+uniq2, cells, solved_pairs, max_rows, max_cols} */
+int wmd_get_last_stats(wmd_handle h, int64_t *values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WMD_B200_H */

@@ -1,0 +1,195 @@
+"""GPU parity tests: libwmd_b200.so (through its C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): WMD within 1e-6 relative of the reference CPU WMD (here the
+expectation is tighter: the integer optimum is unique, so values agree to the last bit unless a
+double rounding differs -- we assert <= 1e-12 relative and report exact-equality counts);
+nBOW counts / weights, statuses and RWMD argmins bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from consistent__style_transfer_b200 import workload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from consistent__style_transfer_b200 import engine
+    return engine
+
+
+def _assert_wmd_equal(got, st, want, wst, rtol=1e-12):
+    assert np.array_equal(st, wst), np.nonzero(st != wst)[0][:10]
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.array_equal(got[~fin], want[~fin])              # +inf where the oracle says +inf
+    np.testing.assert_allclose(got[fin], want[fin], rtol=rtol, atol=0.0)
+
+
+@pytest.mark.parametrize("d", [5, 100, 130, 300])
+def test_normalize_rows_bit_exact(eng_mod, oracle, d):
+    rng = np.random.default_rng(d)
+    raw = rng.standard_normal((257, d)).astype(np.float32) * 3.0
+    e = eng_mod.WMDEngine(raw, normalize=True)
+    want = oracle.init_sims_replace(raw)
+    assert e.table().tobytes() == want.tobytes()
+    e.close()
+
+
+@pytest.mark.parametrize("use_rank", [False, True])
+def test_nbow_bit_exact(eng_mod, oracle, use_rank):
+    V = 500
+    rng = np.random.default_rng(3)
+    table = workload.make_table(V, 16, seed=1)
+    rank = rng.permutation(V).astype(np.int32) if use_rank else None
+    ids, off, _, _ = workload.make_pairs(300, "book", "independent", V=V, seed=4)
+    ids = ids.copy(); ids[rng.random(len(ids)) < 0.1] = -1
+    e = eng_mod.WMDEngine(table, rank=rank)
+    rows, counts, weights, uniq = e.nbow(ids, off)
+    for p in range(300):
+        r, c, w = oracle.nbow(ids[off[p]:off[p + 1]], rank)
+        u = uniq[p]
+        assert u == len(r)
+        a = off[p]
+        assert np.array_equal(rows[a:a + u], r) and np.array_equal(counts[a:a + u], c)
+        assert weights[a:a + u].tobytes() == w.tobytes()
+    e.close()
+
+
+@pytest.mark.parametrize("d,shape,variant,B", [
+    (100, "yelp", "noised", 4000), (300, "yelp", "independent", 4000), (300, "yelp", "noised", 2000),
+    (100, "book", "noised", 1500), (300, "book", "independent", 1000), (7, "yelp", "independent", 500),
+    (130, "yelp", "independent", 500),
+])
+def test_wmd_pairs_match_oracle(eng_mod, oracle, d, shape, variant, B):
+    V = 2000
+    table = workload.make_table(V, d, seed=2)
+    ids1, off1, ids2, off2 = workload.make_pairs(B, shape, variant, V=V, seed=7)
+    rng = np.random.default_rng(5)
+    ids1 = ids1.copy(); ids1[rng.random(len(ids1)) < 0.03] = -1      # OOV tokens
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
+    _assert_wmd_equal(got, st, want, wst)
+    e.close()
+
+
+def test_wmd_pairs_with_rank_and_token_map(eng_mod, oracle):
+    V = 800
+    rng = np.random.default_rng(12)
+    table = workload.make_table(V, 100, seed=3)
+    rank = rng.permutation(V).astype(np.int32)
+    ntok = 1000                                                   # tokenizer ids 0..999, some unmapped
+    tmap = np.full(ntok, -1, np.int32)
+    tmap[rng.permutation(ntok)[:V]] = np.arange(V, dtype=np.int32)
+    t1, off1, t2, off2 = workload.make_pairs(1500, "yelp", "noised", V=ntok, seed=9)
+    e = eng_mod.WMDEngine(table, rank=rank, token_map=tmap)
+    got, st = e.wmd_pairs(t1, off1, t2, off2)
+    want, wst = oracle.batch_wmd(table, tmap[t1], off1, tmap[t2], off2, rank=rank, nthreads=8)
+    _assert_wmd_equal(got, st, want, wst)
+    e.close()
+
+
+def test_early_outs_and_edge_cases(eng_mod, oracle):
+    table = workload.make_table(50, 16, seed=3)
+    table[7] = table[6]
+    docs1 = [[-1], [1], [1, 1], [6], [1, 2], [], [3], [5, 5, 5, 9], [99999]]
+    docs2 = [[1], [], [1], [7], [2, 1], [], [9], [9, 5], [1]]
+    ids1, off1 = workload.to_csr(docs1); ids2, off2 = workload.to_csr(docs2)
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, np.where(ids1 >= 50, -1, ids1).astype(np.int32), off1, ids2, off2)
+    assert list(st) == [1, 1, 2, 3, 0, 1, 0, 0, 1]
+    _assert_wmd_equal(got, st, want, wst)
+    assert got[4] == 0.0
+    # empty batch
+    z = np.zeros(1, np.int64)
+    g0, s0 = e.wmd_pairs(np.zeros(0, np.int32), z, np.zeros(0, np.int32), z)
+    assert g0.shape == (0,) and s0.shape == (0,)
+    # too-long document is an error, not a silent truncation
+    long_ids, long_off = workload.to_csr([[1] * 300])
+    with pytest.raises(RuntimeError):
+        e.wmd_pairs(long_ids, long_off, long_ids, long_off)
+    e.close()
+
+
+@pytest.mark.parametrize("L", [8, 33, 64, 128, 256])
+def test_length_sweep_matches_oracle(eng_mod, oracle, L):
+    V = 10000
+    table = workload.make_table(V, 300, seed=0)
+    B = 96 if L >= 128 else 400
+    ids1, off1, ids2, off2 = workload.make_pairs(B, f"fixed:{L}", "independent", V=V, seed=L)
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
+    _assert_wmd_equal(got, st, want, wst)
+    e.close()
+
+
+def test_rwmd_matches_oracle(eng_mod, oracle):
+    V = 600
+    table = workload.make_table(V, 100, seed=6)
+    ids1, off1, ids2, off2 = workload.make_pairs(400, "book", "independent", V=V, seed=13)
+    e = eng_mod.WMDEngine(table)
+    r = e.rwmd_pairs(ids1, off1, ids2, off2)
+    wmd, _ = e.wmd_pairs(ids1, off1, ids2, off2)
+    for p in range(400):
+        w = oracle.rwmd_pair(table, ids1[off1[p]:off1[p + 1]], ids2[off2[p]:off2[p + 1]])
+        u1, u2 = len(w[3]), len(w[4])
+        assert r["lb"][p] == w[0] and r["l1"][p] == w[1] and r["l2"][p] == w[2]
+        assert np.array_equal(r["argmin_rows"][off1[p]:off1[p] + u1], w[3])
+        assert np.array_equal(r["argmin_cols"][off2[p]:off2[p] + u2], w[4])
+        assert r["lb"][p] <= wmd[p] * (1 + 1e-5) + 1e-9
+    e.close()
+
+
+def test_device_entries_match_host_entry(eng_mod):
+    import torch
+    V = 3000
+    table = workload.make_table(V, 300, seed=8)
+    B = 70000                                                      # > one chunk: exercises both streams
+    ids1, off1, ids2, off2 = workload.make_pairs(B, "yelp", "independent", V=V, seed=21)
+    e = eng_mod.WMDEngine(table)
+    host, hst = e.wmd_pairs(ids1, off1, ids2, off2)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    out, st = e.wmd_pairs_cuda(t(ids1), t(off1), t(ids2), t(off2), 20, 20)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host) and np.array_equal(st.cpu().numpy(), hst)
+    # padded entry: pad id 0 skipped, so shift rows by one through a token map
+    e.set_token_map(np.concatenate([[-1], np.arange(V)]).astype(np.int32))
+    A = np.zeros((B, 20), np.int64); Bm = np.zeros((B, 20), np.int64)
+    for p in range(0, B, 97):                                      # a strided subset keeps the python loop short
+        a = ids1[off1[p]:off1[p + 1]] + 1; b = ids2[off2[p]:off2[p + 1]] + 1
+        A[p, :len(a)] = a; Bm[p, 20 - len(b):] = b                 # pads on either end
+    sel = np.arange(0, B, 97)
+    po, ps = e.wmd_pairs_padded(t(A[sel]), t(Bm[sel]), pad_id=0)
+    torch.cuda.synchronize()
+    assert np.array_equal(po.cpu().numpy(), host[sel]) and np.array_equal(ps.cpu().numpy(), hst[sel])
+    e.close()
+
+
+def test_symmetry_and_permutation_invariance_full_size(eng_mod):
+    """Size-independent properties at the BASELINE shape (no oracle needed)."""
+    table = workload.make_table(10000, 300, seed=0)
+    B = 200000
+    ids1, off1, ids2, off2 = workload.make_pairs(B, "yelp", "independent", V=10000, seed=1)
+    e = eng_mod.WMDEngine(table)
+    v12, s12 = e.wmd_pairs(ids1, off1, ids2, off2)
+    v21, s21 = e.wmd_pairs(ids2, off2, ids1, off1)
+    assert np.array_equal(s12, s21)
+    fin = np.isfinite(v12)
+    np.testing.assert_allclose(v12[fin], v21[fin], rtol=1e-12)
+    # reversing the token order inside every document changes nothing (bags of words)
+    lens = np.diff(off1)
+    pos = np.arange(len(ids1)) - np.repeat(off1[:-1], lens)
+    rev = np.repeat(off1[:-1], lens) + (np.repeat(lens, lens) - 1 - pos)
+    vp, _ = e.wmd_pairs(ids1[rev], off1, ids2, off2)
+    assert np.array_equal(vp, v12)
+    # identical documents -> exactly 0.0 (or status 2 for one-token vocabularies)
+    v0, s0 = e.wmd_pairs(ids1, off1, ids1, off1)
+    assert np.all(v0 == 0.0) and set(np.unique(s0)) <= {0, 2}
+    e.close()
