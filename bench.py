@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- WMD sentence-pairs/s on the Yelp-shape synthetic batch (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's B200 engine
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path (nBOW -> gather -> cost tile -> exact EMD) over one batch of
+synthetic pairs: 1 M Yelp-shape pairs per GPU (len 1..20, d=300, V=10k, `independent` variant =
+worst case).  Weak scaling: every rank scores its own 1 M pairs; nothing but the
+timing scalar crosses NCCL (pairs are independent -- BASELINE north_star / SURVEY 8(e)).
+
+value  = pairs/s with ids/offsets already resident in HBM (wmd_pairs_dev), CUDA-event timed.
+e2e    = pairs/s through the host entry wmd_pairs_host on PINNED HOST buffers: H2D of ids+offsets and
+         D2H of scores+status are inside the timed region of every step.
+roofline.achieved = algorithmic bytes of the step (4(n1+n2) + 4d(u1+u2) + 8 per pair,
+         summed from the engine's own counters) / the dominant kernel's summed launch time in the
+         step, from CUDA events recorded on the kernels' own streams during the timed steps.
+cpu_baseline / --impl reference = oracle/wmd_oracle.py's gensim-shaped python loop + C emd_hat
+         (the reference itself cannot be installed: gensim and pyemd are absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from consistent__style_transfer_b200 import workload  # noqa: E402
+
+METRIC = "wmd_sentence_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
+    ap.add_argument("--shape", default="yelp")
+    ap.add_argument("--variant", default="independent", choices=["independent", "noised"])
+    ap.add_argument("--d", type=int, default=300)
+    ap.add_argument("--vocab", type=int, default=10_000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.shape}-shape {a.variant} pairs, len<=20, d={a.d}, V={a.vocab}, {a.pairs} pairs/GPU/step"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference path, run in worker processes (one per core)
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(table, ids1, off1, ids2, off2):
+    from oracle import wmd_oracle
+    words = ["w%06d" % i for i in range(table.shape[0])]      # zero-padded: string order == row order
+    _W.update(kv=wmd_oracle.KeyedVectorsOracle(words, table), words=words, ids1=ids1, off1=off1, ids2=ids2, off2=off2)
+    wmd_oracle.lib()
+
+
+def _cpu_worker(span):
+    lo, hi = span
+    kv, words, ids1, off1, ids2, off2 = (_W[k] for k in ("kv", "words", "ids1", "off1", "ids2", "off2"))
+    t0 = time.perf_counter()
+    acc = 0.0
+    for p in range(lo, hi):
+        d1 = [words[t] for t in ids1[off1[p]:off1[p + 1]]]
+        d2 = [words[t] for t in ids2[off2[p]:off2[p + 1]]]
+        v = kv.wmdistance(d1, d2)                                 # the reference's per-pair call (src/wmd.py:32)
+        if v != float("inf"):
+            acc += v
+    return time.perf_counter() - t0, hi - lo, acc
+
+
+class CpuPool:
+    """Worker processes (fork, one per core) running the reference-shaped python loop."""
+
+    def __init__(self, table, pairs, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(table,) + tuple(pairs))
+        self.pool.map(_cpu_worker, [(0, 1)] * cores)             # touch every worker once
+
+    def run(self, lo, hi):
+        bounds = np.linspace(lo, hi, self.cores + 1).astype(int)
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, [(int(bounds[i]), int(bounds[i + 1])) for i in range(self.cores)], chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_c_port(table, pairs, n_sample, cores):
+    from oracle import wmd_oracle
+    ids1, off1, ids2, off2 = pairs
+    n = min(n_sample, len(off1) - 1)
+    a1, o1 = ids1[:off1[n]], off1[:n + 1]
+    a2, o2 = ids2[:off2[n]], off2[:n + 1]
+    wmd_oracle.batch_wmd(table, a1[:o1[64]], o1[:65], a2[:o2[64]], o2[:65], nthreads=cores)
+    t0 = time.perf_counter()
+    wmd_oracle.batch_wmd(table, a1, o1, a2, o2, nthreads=cores)
+    return n / (time.perf_counter() - t0)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    table = workload.make_table(a.vocab, a.d, seed=0)
+    per_step = a.cpu_sample or 1000 * cores
+    pairs = workload.make_pairs(per_step * (a.steps + a.warmup), a.shape, a.variant, V=a.vocab, seed=1)
+    pool = CpuPool(table, pairs, cores)
+    times = []
+    for s_ in range(a.warmup + a.steps):
+        dt = pool.run(s_ * per_step, (s_ + 1) * per_step)
+        if s_ >= a.warmup:
+            times.append(dt)
+    pool.close()
+    total = sum(times)
+    value = per_step * a.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_pairs_per_step": per_step,
+                   "note": "reference cannot be installed (gensim/pyemd absent); oracle port of its CPU path"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} pairs/step of the same workload, python per-pair loop + C emd_hat, "
+                                   f"{cores} worker processes, wall time per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(a.gpus, world)
+
+    table = workload.make_table(a.vocab, a.d, seed=0)
+    pairs = workload.make_pairs(a.pairs, a.shape, a.variant, V=a.vocab, seed=1 + rank)
+    ids1, off1, ids2, off2 = pairs
+    ml1, ml2 = int(np.diff(off1).max()), int(np.diff(off2).max())
+
+    # CPU baseline first (fork-based workers must start before CUDA is initialised)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = a.cpu_sample or 1500 * cores
+        pool = CpuPool(table, pairs, cores)
+        wall = pool.run(0, n_sample)
+        pool.close()
+        v = n_sample / wall
+        c_port = cpu_c_port(table, pairs, 40000, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n_sample} pairs of the same workload split over {cores} worker processes: "
+                         f"gensim-shaped python per-pair loop (numpy float32 per cell) + C emd_hat; {wall:.1f}s wall",
+               "compiled_c_port_value": c_port,
+               "compiled_c_port_note": f"all-C oracle (oracle/wmd_oracle.c) on 40000 pairs, {cores} pthreads"}
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from consistent__style_transfer_b200.engine import WMDEngine
+    eng = WMDEngine(table, device=local)
+
+    d_ids1 = torch.from_numpy(ids1).to(dev); d_off1 = torch.from_numpy(off1).to(dev)
+    d_ids2 = torch.from_numpy(ids2).to(dev); d_off2 = torch.from_numpy(off2).to(dev)
+    d_out = torch.empty(a.pairs, dtype=torch.float64, device=dev)
+    d_st = torch.empty(a.pairs, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step():
+        eng.wmd_pairs_cuda(d_ids1, d_off1, d_ids2, d_off2, ml1, ml2, out=d_out, status=d_st)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    for _ in range(a.warmup):
+        flush.fill_(1)
+        dev_step()
+    barrier()
+    eng.set_profiling(True)
+    eng.profile(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(1)                                                     # L2 flush, outside the event pair
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dev_step()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = sum(step_ms)
+    prof = eng.profile(reset=True)
+    eng.set_profiling(False)
+    stats = eng.last_stats()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n_gpus * a.pairs * a.steps / (total_ms_max / 1e3)
+
+    # ---- e2e: pinned host buffers through the host entry --------------------------------------
+    h_ids1 = torch.from_numpy(ids1).pin_memory(); h_off1 = torch.from_numpy(off1).pin_memory()
+    h_ids2 = torch.from_numpy(ids2).pin_memory(); h_off2 = torch.from_numpy(off2).pin_memory()
+    h_out = torch.empty(a.pairs, dtype=torch.float64).pin_memory()
+    h_st = torch.empty(a.pairs, dtype=torch.int32).pin_memory()
+
+    def host_step():
+        eng.wmd_pairs_ptr(h_ids1.data_ptr(), h_off1.data_ptr(), h_ids2.data_ptr(), h_off2.data_ptr(), a.pairs,
+                          h_out.data_ptr(), h_st.data_ptr())
+
+    for _ in range(a.warmup):
+        host_step()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(a.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_step()                                                        # returns after the D2H of the scores
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * a.pairs * a.steps / float(t.item())
+    h2d = int(ids1.nbytes + ids2.nbytes + off1.nbytes + off2.nbytes)
+    d2h = int(a.pairs * (8 + 4))
+    same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes_step = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * a.pairs
+    kern = {k: v for k, v in prof.items() if v["launches"] > 0}
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    dom_ms_step = kern[dom]["ms"] / a.steps
+    achieved = alg_bytes_step / (dom_ms_step / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes_step,
+                "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in kern.items()},
+                "launches_per_step": {k: v["launches"] // a.steps for k, v in kern.items()},
+                "whole_step_achieved": alg_bytes_step / (total_ms / a.steps / 1e3) / 1e9}
+    launches = sum(v["launches"] for v in kern.values())
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "pairs_per_gpu": a.pairs, "global_pairs": n_gpus * a.pairs,
+                       "mean_len": float(stats["tokens"]) / (2 * a.pairs), "cost": "float32 numpy-order (bit-exact)",
+                       "emd": "pyemd 1e6-grid integer optimum, exact", "l2": "256 MiB flush write between timed steps",
+                       "parallelism": f"pairs sharded over {n_gpus} GPU(s), no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timing": "perf_counter around the synchronous wmd_pairs_host call on pinned buffers",
+                    "matches_device_path": same},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

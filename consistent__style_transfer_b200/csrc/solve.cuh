@@ -161,6 +161,187 @@ __device__ long long transport_solve(int m, int nc, int ldc, const int *cost, in
     return warp_sum_ll(tot);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Class A (m <= 32 rows, nc <= 32 columns incl. the dummy): the same primal-dual method with the
+// whole dual / tree state in registers.  Lane L is both row L and column L:
+//   as a column: potential v, remaining deficit, tentative distance minv, tree predecessor way,
+//                colmask = bitmask of rows currently shipping into this column
+//   as a row:    potential u, tree distance rdist, predecessor column rpred
+// The tree and the used-column set are warp-uniform bitmasks, so "which rows join the tree when
+// column j saturates" is one shuffle of colmask instead of a scan of the flow matrix.  Only the
+// dense int32 cost and flow matrices live in shared memory.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t solve_small_smem_per_warp(int mr, int mc, int ldc)
+{
+    return ((size_t)2 * mr * ldc + mr + mc) * 4;
+}
+
+__device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost, int *flow,
+                                                           int supply, int deficit, int lane)
+{
+    int u = 0, v = 0;
+    unsigned colmask = 0;
+    for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0;
+    __syncwarp();
+    const bool iscol = lane < nc;
+    for (int r = 0; r < m; ++r) {
+        int sup = __shfl_sync(kFull, supply, r);
+        while (sup > 0) {
+            unsigned used = 0, tree = 1u << r;
+            int rdist = 0, rpred = -1;
+            int minv = kIntInf, way = r;
+            {
+                const int ur = __shfl_sync(kFull, u, r);
+                if (iscol) minv = cost[r * ldc + lane] - ur - v;
+            }
+            int delta, jl, def;
+            for (;;) {
+                const int key = ((used >> lane) & 1u) ? kIntInf : minv;
+                delta = __reduce_min_sync(kFull, key);
+                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
+                jl = __ffs(__ballot_sync(kFull, key == delta)) - 1;
+                used |= 1u << jl;
+                def = __shfl_sync(kFull, deficit, jl);
+                if (def > 0) break;
+                unsigned nr = __shfl_sync(kFull, colmask, jl) & ~tree;   // rows shipping into the saturated column
+                tree |= nr;
+                if ((nr >> lane) & 1u) { rdist = delta; rpred = jl; }
+                while (nr) {
+                    const int i = __ffs(nr) - 1;
+                    nr &= nr - 1;
+                    const int ui = __shfl_sync(kFull, u, i);
+                    if (iscol && !((used >> lane) & 1u)) {
+                        const int cand = delta + cost[i * ldc + lane] - ui - v;
+                        if (cand < minv) { minv = cand; way = i; }
+                    }
+                }
+            }
+            if ((tree >> lane) & 1u) u += delta - rdist;         // dual update (tree nodes only)
+            if ((used >> lane) & 1u) v -= delta - minv;
+            int amt = min(sup, def);
+            for (int j = jl;;) {                                 // bottleneck along the tree path jl -> r
+                const int i = __shfl_sync(kFull, way, j);
+                if (i == r) break;
+                const int jp = __shfl_sync(kFull, rpred, i);
+                amt = min(amt, flow[i * ldc + jp]);
+                j = jp;
+            }
+            for (int j = jl;;) {                                 // push amt; each column's lane owns its flow entries
+                const int i = __shfl_sync(kFull, way, j);
+                if (lane == j) { flow[i * ldc + j] += amt; colmask |= 1u << i; }
+                if (i == r) break;
+                const int jp = __shfl_sync(kFull, rpred, i);
+                if (lane == jp) {
+                    const int f = flow[i * ldc + jp] - amt;
+                    flow[i * ldc + jp] = f;
+                    if (f == 0) colmask &= ~(1u << i);
+                }
+                j = jp;
+            }
+            __syncwarp();
+            sup -= amt;
+            if (lane == jl) deficit -= amt;
+        }
+    }
+    long long tot = 0;
+    if (iscol)
+        for (int i = 0; i < m; ++i) tot += (long long)flow[i * ldc + lane] * (long long)cost[i * ldc + lane];
+    return warp_sum_ll(tot);
+}
+
+__global__ void __launch_bounds__(256)
+emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
+{
+    extern __shared__ __align__(16) int smem_i[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ldc = A.ldc;
+    int *cost = smem_i + (size_t)wib * (solve_small_smem_per_warp(A.mr, A.mc, ldc) / 4);
+    int *flow = cost + A.mr * ldc;
+    int *sridx = flow + A.mr * ldc;
+    int *scidx = sridx + A.mr;
+    int64_t tok1, tok2;
+    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = (int)atomicAdd(A.counter, 8u);
+        q0 = __shfl_sync(kFull, q0, 0);
+        if (q0 >= A.npairs) break;
+        const int q1 = min(A.npairs, q0 + 8);
+        for (int q = q0; q < q1; ++q) {
+            const int meta = A.meta[q];
+            if ((meta & 7) != kClsA) continue;
+            const int64_t p = A.p0 + q;
+            const float maxc_f = A.maxc[q];
+            if (!(maxc_f > 0.f)) {                               // S4: all-zero distance matrix
+                if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+                continue;
+            }
+            const int uu = A.u12[q];
+            const int u1 = uu & 0xffff, u2 = uu >> 16;
+            const bool swap = (meta & kMetaSwap) != 0;
+            int64_t a1, a2; int l;
+            doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
+            const int32_t *ipR = swap ? A.ip2 + (a2 - tok2) : A.ip1 + (a1 - tok1);   // supplying side
+            const int32_t *ipC = swap ? A.ip1 + (a1 - tok1) : A.ip2 + (a2 - tok2);
+            const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
+            int m = 0, n = 0, sumR = 0, sumC = 0;
+            for (int base = 0; base < uR; base += kWarp) {       // compact the residual rows: (mass << 8) | index
+                const int i = base + lane;
+                const int x = i < uR ? ipR[i] : 0;
+                const unsigned bal = __ballot_sync(kFull, x > 0);
+                if (x > 0) sridx[m + __popc(bal & ((1u << lane) - 1))] = (x << 8) | i;
+                m += __popc(bal);
+                sumR += x;
+            }
+            for (int base = 0; base < uC; base += kWarp) {
+                const int j = base + lane;
+                const int x = j < uC ? ipC[j] : 0;
+                const unsigned bal = __ballot_sync(kFull, x > 0);
+                if (x > 0) scidx[n + __popc(bal & ((1u << lane) - 1))] = (x << 8) | j;
+                n += __popc(bal);
+                sumC += x;
+            }
+            sumR = warp_sum(sumR); sumC = warp_sum(sumC);
+            __syncwarp();
+            const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+            long long opt = 0;
+            if (n > 0 && m > 0) {
+                const int diff = sumR - sumC;                    // >= 0 by the choice of the supplying side
+                const int nc = n + (diff > 0 ? 1 : 0);
+                const int packedR = lane < m ? sridx[lane] : 0;
+                const int packedC = lane < n ? scidx[lane] : 0;
+                const int supply = packedR >> 8;
+                const int deficit = lane < n ? (packedC >> 8) : (lane == n ? diff : 0);
+                // quantised costs of the residual sub-tile (S6(d)); the dummy column costs 0
+                const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+                const int j = packedC & 0xff;
+                for (int rI = 0; rI < m; ++rI) {
+                    const int i = __shfl_sync(kFull, packedR, rI) & 0xff;
+                    int ic = 0;
+                    if (lane < n) {
+                        const float dv = swap ? tile[j * u2 + i] : tile[i * u2 + j];
+                        ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                    }
+                    if (lane < nc) cost[rI * ldc + lane] = ic;
+                }
+                __syncwarp();
+                opt = transport_solve_small(m, nc, ldc, cost, flow, supply, deficit, lane);
+            }
+            if (lane == 0) {
+                double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
+                dist = __ddiv_rn(dist, A.pqn[q]);                 // S6(f)
+                dist = __ddiv_rn(dist, Cn);
+                dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
+                A.out[p] = dist;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int KC>
 __global__ void __launch_bounds__(256)
 emd_solve_kernel(const __grid_constant__ SolveArgs A)

@@ -247,7 +247,8 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         S.counter = W.counters.as<unsigned int>() + cls;
         S.out = O.out; S.status = O.status;
         int wpb = 8;
-        size_t per_warp = solve_smem_per_warp(S.mr, S.mc, S.ldc, S.use_global);
+        size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
+                                       : solve_smem_per_warp(S.mr, S.mc, S.ldc, S.use_global);
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (cls == kClsC ? 2 : 8));
@@ -259,8 +260,8 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         }
         Prof pr(E, WMD_K_SOLVE, st);
         if (cls == kClsA) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_kernel<1><<<grid, wpb * 32, smem, st>>>(S);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_small_kernel<<<grid, wpb * 32, smem, st>>>(S);
         } else if (cls == kClsB) {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             emd_solve_kernel<2><<<grid, wpb * 32, smem, st>>>(S);
