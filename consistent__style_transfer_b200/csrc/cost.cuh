@@ -4,23 +4,32 @@
 //     D[i, j] = sqrt(np_sum((wv[t_i] - wv[t_j]) ** 2))          (float32, numpy summation order)
 // for every unique doc1 token i and unique doc2 token j of a pair, plus the tile maximum
 // (pyemd's maxC, S6(b)).  Bit-exact with numpy: every subtract, multiply, add and the square
-// root are separately rounded float32 operations (no FMA), accumulated in numpy's
+// root are separately rounded float32 operations (no FMA contraction), accumulated in numpy's
 // FLOAT_pairwise_sum order -- eight strided accumulators per leaf block, leaves combined by
 // the recursion tree that SumPlan flattens.
 //
-// Mapping.  A CTA stages the table rows of a *group* of consecutive pairs in shared memory
-// (each row read from L2/HBM exactly once per pair, 128-bit coalesced loads), then all threads
-// sweep a flattened list of lane tasks.  A task is half of a 2x2 cell tile: two adjacent lanes
-// own the accumulator quads r[0..3] and r[4..7] of the same four cells and meet with one
-// shuffle per leaf, so shared-memory traffic is 4 LDS.128 per 48 FP32 operations.
+// Structure (sm_100a).  One persistent CTA per SM runs a producer/consumer ring:
+//   * warp 0 (producer) walks its slice of pairs, packs consecutive pairs into a stage
+//     ("group"), and gathers their table rows HBM/L2 -> shared memory with 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx), one copy per row, each row fetched once per pair;
+//   * the consumer warps wait on the stage's "full" mbarrier, pull tile tasks from a shared
+//     counter, and release the stage through its "empty" mbarrier; they never barrier with each
+//     other, so a warp that runs out of tiles in one stage starts on the next.
+// A tile task is a 2x4 block of cells owned by 2*PL adjacent lanes: lane (leaf l, half h) keeps
+// the accumulator quads r[4h..4h+3] of leaf block l for all eight cells, i.e. 6 LDS.128 per 96
+// float operations, which balances the 128 B/clk shared-memory port against the FP32 pipe.
+// The float math is issued as packed FADD2/FFMA2 (sub.f32x2, fma.f32x2 with a -0.0 addend that
+// ptxas cannot see, add.f32x2): identical IEEE roundings, half the issue slots.
 #pragma once
 #include "common.cuh"
 
 namespace wmd {
 
-constexpr int kCostThreads = 256;
+constexpr int kCostConsumerWarps = 8;
+constexpr int kCostThreads = 32 * (1 + kCostConsumerWarps);
 constexpr int kGroupMax = 32;        // pairs per staged group
 constexpr int kPlanDepth = 8;
+constexpr int kMaxStages = 4;
 
 struct CostArgs {
     Vocab vc;
@@ -29,8 +38,13 @@ struct CostArgs {
     int64_t p0;                      // first pair of this chunk
     int32_t npairs;                  // pairs in this chunk
     int32_t tb;                      // max rows per side of a staged unit (<= 32)
-    int32_t rcap;                    // row capacity of the staging buffer
-    int32_t ldr;                     // floats between staged rows (multiple of 4; ldr/4 odd)
+    int32_t rcap;                    // row capacity of one stage
+    int32_t ldr;                     // floats between staged rows (multiple of 4)
+    int32_t stages;                  // ring depth (2..kMaxStages)
+    int32_t pl;                      // leaf blocks processed in parallel by one tile (1, 2 or 4)
+    int32_t rowbytes;                // bytes copied per row (ld * 4, multiple of 16)
+    int32_t _pad;
+    unsigned long long negzero2;     // 0x8000000080000000: (-0.0f, -0.0f), opaque to ptxas
     const int32_t *rows1, *rows2;    // from K1
     const int32_t *u12;
     float *tiles;                    // [npairs, tile_stride]
@@ -41,235 +55,380 @@ struct CostArgs {
 struct CostUnit {
     int32_t q;                       // pair (chunk-local)
     int32_t rowbase;                 // first staged row
-    int32_t i0, ni, j0, nj;          // sub-block of the pair's tile
+    int32_t i0, ni, j0, nj;          // sub-block of the pair's tile (doc1 rows x doc2 rows)
     int32_t u2;                      // tile row pitch
-    int32_t taskbase;
+    int32_t tilebase;                // first tile task of the unit inside its group
+    int32_t tr;                      // 1: the 2-side of the 2x4 tile runs along doc2
+    int32_t _pad;
     int64_t o1, o2;                  // token-slot offsets of the pair
 };
 
-__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > (1ll << 33)) __trap();       // ~4 s: a protocol bug must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_row_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-__device__ __forceinline__ void sq_acc_init(float4 &acc, const float4 a, const float4 b)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// x*x rounded once: fma with a -0.0 addend held in a register ptxas cannot fold (it would
+// otherwise turn mul+add into one FFMA2 and lose numpy's intermediate rounding)
+__device__ __forceinline__ f32x2 sq2(f32x2 a, f32x2 nz) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(nz)); return r; }
+__device__ __forceinline__ float lo_f(f32x2 a) { return __uint_as_float((unsigned)(a & 0xffffffffull)); }
+__device__ __forceinline__ float hi_f(f32x2 a) { return __uint_as_float((unsigned)(a >> 32)); }
+
+struct Q4 { f32x2 lo, hi; };          // four consecutive floats
+__device__ __forceinline__ Q4 ldq(const float *p)
 {
-    float t;
-    t = __fsub_rn(a.x, b.x); acc.x = __fmul_rn(t, t);
-    t = __fsub_rn(a.y, b.y); acc.y = __fmul_rn(t, t);
-    t = __fsub_rn(a.z, b.z); acc.z = __fmul_rn(t, t);
-    t = __fsub_rn(a.w, b.w); acc.w = __fmul_rn(t, t);
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    return Q4{ v.x, v.y };
 }
-__device__ __forceinline__ void sq_acc(float4 &acc, const float4 a, const float4 b)
+__device__ __forceinline__ float quad_sum(const Q4 a)
 {
-    float t;
-    t = __fsub_rn(a.x, b.x); acc.x = __fadd_rn(acc.x, __fmul_rn(t, t));
-    t = __fsub_rn(a.y, b.y); acc.y = __fadd_rn(acc.y, __fmul_rn(t, t));
-    t = __fsub_rn(a.z, b.z); acc.z = __fadd_rn(acc.z, __fmul_rn(t, t));
-    t = __fsub_rn(a.w, b.w); acc.w = __fadd_rn(acc.w, __fmul_rn(t, t));
-}
-__device__ __forceinline__ float quad_sum(const float4 a)
-{
-    return __fadd_rn(__fadd_rn(a.x, a.y), __fadd_rn(a.z, a.w));
+    return __fadd_rn(__fadd_rn(lo_f(a.lo), hi_f(a.lo)), __fadd_rn(lo_f(a.hi), hi_f(a.hi)));
 }
 
-// One leaf block of numpy's pairwise sum for the four cells (a0,b0) (a0,b1) (a1,b0) (a1,b1).
-// `half` selects accumulators r[0..3] (0) or r[4..7] (1); both lanes of a pair return the same sums.
-__device__ __forceinline__ void leaf_2x2(const float *a0, const float *a1, const float *b0, const float *b1,
-                                         int start, int len, int half, float (&res)[4])
+// One leaf block [start, start+len) of numpy's pairwise sum for the 2x4 cells (a_r, b_c).
+// half selects accumulators r[0..3] or r[4..7]; the two lanes meet with one shuffle.
+__device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float *const (&b)[4], int start, int len,
+                                         int half, f32x2 nz, float (&res)[8])
 {
     if (len < 8) {                                     // numpy: plain sequential loop
-        res[0] = res[1] = res[2] = res[3] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) res[c] = 0.f;
         for (int e = start; e < start + len; ++e) {
-            const float x0 = a0[e], x1 = a1[e], y0 = b0[e], y1 = b1[e];
-            float t;
-            t = __fsub_rn(x0, y0); res[0] = __fadd_rn(res[0], __fmul_rn(t, t));
-            t = __fsub_rn(x0, y1); res[1] = __fadd_rn(res[1], __fmul_rn(t, t));
-            t = __fsub_rn(x1, y0); res[2] = __fadd_rn(res[2], __fmul_rn(t, t));
-            t = __fsub_rn(x1, y1); res[3] = __fadd_rn(res[3], __fmul_rn(t, t));
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float t = __fsub_rn(a[r][e], b[c][e]);
+                    res[r * 4 + c] = __fadd_rn(res[r * 4 + c], __fmul_rn(t, t));
+                }
         }
         return;
     }
     const int nfull = len - (len & 7);
     int e = start + 4 * half;
-    float4 c00, c01, c10, c11;
-    {
-        const float4 x0 = lds4(a0 + e), x1 = lds4(a1 + e), y0 = lds4(b0 + e), y1 = lds4(b1 + e);
-        sq_acc_init(c00, x0, y0); sq_acc_init(c01, x0, y1); sq_acc_init(c10, x1, y0); sq_acc_init(c11, x1, y1);
-    }
     const int eend = start + nfull;
+    Q4 acc[8];
+    {
+        Q4 x[2], y[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y[c] = ldq(b[c] + e);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[r * 4 + c].lo = sq2(sub2(x[r].lo, y[c].lo), nz);
+                acc[r * 4 + c].hi = sq2(sub2(x[r].hi, y[c].hi), nz);
+            }
+    }
 #pragma unroll 2
     for (e += 8; e < eend; e += 8) {
-        const float4 x0 = lds4(a0 + e), x1 = lds4(a1 + e), y0 = lds4(b0 + e), y1 = lds4(b1 + e);
-        sq_acc(c00, x0, y0); sq_acc(c01, x0, y1); sq_acc(c10, x1, y0); sq_acc(c11, x1, y1);
-    }
-    float p[4] = { quad_sum(c00), quad_sum(c01), quad_sum(c10), quad_sum(c11) };
+        Q4 x[2], y[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float o = __shfl_xor_sync(kFull, p[c], 1);
-        res[c] = half ? __fadd_rn(o, p[c]) : __fadd_rn(p[c], o);   // (r0+r1+r2+r3) + (r4+..+r7)
-    }
-    for (int t = eend; t < start + len; ++t) {         // the len % 8 tail, sequential
-        const float x0 = a0[t], x1 = a1[t], y0 = b0[t], y1 = b1[t];
-        float s;
-        s = __fsub_rn(x0, y0); res[0] = __fadd_rn(res[0], __fmul_rn(s, s));
-        s = __fsub_rn(x0, y1); res[1] = __fadd_rn(res[1], __fmul_rn(s, s));
-        s = __fsub_rn(x1, y0); res[2] = __fadd_rn(res[2], __fmul_rn(s, s));
-        s = __fsub_rn(x1, y1); res[3] = __fadd_rn(res[3], __fmul_rn(s, s));
-    }
-}
-
-// sqrt(sum((a-b)^2)) for the four cells of a lane task, numpy order.
-__device__ __forceinline__ void dist_2x2(const SumPlan &plan, const float *a0, const float *a1,
-                                         const float *b0, const float *b1, int half, float (&out)[4])
-{
-    float st[kPlanDepth][4];
-    int sp = 0;
-    for (int o = 0; o < plan.nops; ++o) {
-        float r[4];
-        leaf_2x2(a0, a1, b0, b1, plan.start[o], plan.len[o], half, r);
+        for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) st[sp][c] = r[c];
-        ++sp;
-        for (int k = 0; k < plan.adds[o]; ++k) {
-            --sp;
+        for (int c = 0; c < 4; ++c) y[c] = ldq(b[c] + e);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) st[sp - 1][c] = __fadd_rn(st[sp - 1][c], st[sp][c]);
-        }
-    }
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = __fsqrt_rn(st[0][c]);
-}
-
-// Stage `nrows` table rows (ids from K1) of unit `un` and run its tasks. Shared by both kernels.
-__device__ __forceinline__ void stage_rows(const CostArgs &A, const CostUnit *units, int nunits, int total_rows,
-                                           float *rowsbuf)
-{
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int d4 = A.vc.d >> 2;
-    for (int rr = wib; rr < total_rows; rr += wpb) {
-        int g = 0;
-        while (g + 1 < nunits && units[g + 1].rowbase <= rr) ++g;
-        const CostUnit &un = units[g];
-        const int local = rr - un.rowbase;
-        int row;
-        if (local < un.ni) row = A.rows1[un.o1 + un.i0 + local];
-        else               row = A.rows2[un.o2 + un.j0 + (local - un.ni)];
-        const float4 *src = reinterpret_cast<const float4 *>(A.vc.table + (int64_t)row * A.vc.ld);
-        float4 *dst = reinterpret_cast<float4 *>(rowsbuf + (size_t)rr * A.ldr);
-        for (int k = lane; k < d4; k += kWarp) dst[k] = __ldg(src + k);
-        const int rem = A.vc.d & 3;                    // d not a multiple of 4: scalar tail
-        if (lane < rem) rowsbuf[(size_t)rr * A.ldr + 4 * d4 + lane] = __ldg(A.vc.table + (int64_t)row * A.vc.ld + 4 * d4 + lane);
-    }
-}
-
-__device__ __forceinline__ void run_tasks(const CostArgs &A, const CostUnit *units, int nunits, int total_tasks,
-                                          const float *rowsbuf, unsigned *umax)
-{
-    const int tid = threadIdx.x;
-    for (int tbase = 0; tbase < total_tasks; tbase += blockDim.x) {
-        int t = tbase + tid;
-        const bool live = t < total_tasks;
-        if (!live) t = (tid & 1);                      // clamp, keep the lane pair together
-        int g = 0;
-        while (g + 1 < nunits && units[g + 1].taskbase <= t) ++g;
-        const CostUnit &un = units[g];
-        const int local = t - un.taskbase;
-        const int half = local & 1;
-        const int tile = local >> 1;
-        const int TI = (un.ni + 1) >> 1, TJ = (un.nj + 1) >> 1;
-        const int ti = tile / TJ, tj = tile - ti * TJ;
-        const int i0 = ti, i1 = ti + TI, j0 = tj, j1 = tj + TJ;
-        const bool vi1 = i1 < un.ni, vj1 = j1 < un.nj;
-        const float *a0 = rowsbuf + (size_t)(un.rowbase + i0) * A.ldr;
-        const float *a1 = rowsbuf + (size_t)(un.rowbase + (vi1 ? i1 : i0)) * A.ldr;
-        const float *b0 = rowsbuf + (size_t)(un.rowbase + un.ni + j0) * A.ldr;
-        const float *b1 = rowsbuf + (size_t)(un.rowbase + un.ni + (vj1 ? j1 : j0)) * A.ldr;
-        float v[4];
-        dist_2x2(A.plan, a0, a1, b0, b1, half, v);
-        if (live) {
-            float *tile_p = A.tiles + (int64_t)un.q * A.tile_stride;
-            float mx = 0.f;
-            // half 0 stores row i0, half 1 stores row i1 (both lanes hold all four values)
-            if (half == 0) {
-                float *rp = tile_p + (int64_t)(un.i0 + i0) * un.u2 + un.j0;
-                rp[j0] = v[0]; mx = v[0];
-                if (vj1) { rp[j1] = v[1]; mx = fmaxf(mx, v[1]); }
-            } else if (vi1) {
-                float *rp = tile_p + (int64_t)(un.i0 + i1) * un.u2 + un.j0;
-                rp[j0] = v[2]; mx = v[2];
-                if (vj1) { rp[j1] = v[3]; mx = fmaxf(mx, v[3]); }
+            for (int c = 0; c < 4; ++c) {
+                acc[r * 4 + c].lo = add2(acc[r * 4 + c].lo, sq2(sub2(x[r].lo, y[c].lo), nz));
+                acc[r * 4 + c].hi = add2(acc[r * 4 + c].hi, sq2(sub2(x[r].hi, y[c].hi), nz));
             }
-            atomicMax(&umax[g], __float_as_uint(mx));   // distances are >= 0: uint order == float order
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float p = quad_sum(acc[c]);
+        const float o = __shfl_xor_sync(kFull, p, 1);
+        res[c] = half ? __fadd_rn(o, p) : __fadd_rn(p, o);       // (r0+r1+r2+r3) + (r4+..+r7)
+    }
+    for (int t = eend; t < start + len; ++t) {                    // the len % 8 tail, sequential
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float s = __fsub_rn(a[r][t], b[c][t]);
+                res[r * 4 + c] = __fadd_rn(res[r * 4 + c], __fmul_rn(s, s));
+            }
+    }
+}
+
+// The eight distances of one tile task. PL = 1: the lane pair walks the whole postfix program;
+// PL = 2 / 4: leaf l of a balanced tree is summed by lane pair l and the tree is closed by shuffles.
+template <int PL>
+__device__ __forceinline__ void dist_2x4(const CostArgs &A, const float *const (&a)[2], const float *const (&b)[4],
+                                         int sub, float (&out)[8])
+{
+    const int half = sub & 1;
+    if (PL == 1) {
+        float st[kPlanDepth][8];
+        int sp = 0;
+        for (int o = 0; o < A.plan.nops; ++o) {
+            float r[8];
+            leaf_2x4(a, b, A.plan.start[o], A.plan.len[o], half, A.negzero2, r);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) st[sp][c] = r[c];
+            ++sp;
+            for (int k = 0; k < A.plan.adds[o]; ++k) {
+                --sp;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) st[sp - 1][c] = __fadd_rn(st[sp - 1][c], st[sp][c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = __fsqrt_rn(st[0][c]);
+    } else {
+        const int l = sub >> 1;
+        float r[8];
+        leaf_2x4(a, b, A.plan.start[l], A.plan.len[l], half, A.negzero2, r);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float o = __shfl_xor_sync(kFull, r[c], 2);
+            r[c] = (l & 1) ? __fadd_rn(o, r[c]) : __fadd_rn(r[c], o);          // L0+L1, L2+L3
+            if (PL == 4) {
+                o = __shfl_xor_sync(kFull, r[c], 4);
+                r[c] = (l & 2) ? __fadd_rn(o, r[c]) : __fadd_rn(r[c], o);      // (L0+L1)+(L2+L3)
+            }
+            out[c] = __fsqrt_rn(r[c]);
         }
     }
 }
 
-// Small pairs (u1 <= tb and u2 <= tb): persistent CTAs, each owning a contiguous slice of pairs.
-__global__ void __launch_bounds__(kCostThreads)
+__device__ __forceinline__ int unit_tiles(int ni, int nj, int tr)
+{
+    const int na = tr ? nj : ni, nb = tr ? ni : nj;
+    return ((na + 1) >> 1) * ((nb + 3) >> 2);
+}
+__device__ __forceinline__ int pick_orientation(int ni, int nj)
+{
+    const int p0 = ((ni + 1) >> 1) * 2 * ((nj + 3) >> 2) * 4;      // padded cells, 2-side along doc1
+    const int p1 = ((nj + 1) >> 1) * 2 * ((ni + 3) >> 2) * 4;
+    return p1 < p0 ? 1 : 0;
+}
+
+// Executes one warp-wide batch of tile tasks [t0, t0 + 32 / (2 PL)) of a group.
+template <int PL>
+__device__ __forceinline__ void run_tile_batch(const CostArgs &A, const CostUnit *units, int nunits, int ntiles, int t0,
+                                               const float *rowsbuf, unsigned *umax)
+{
+    constexpr int LPT = 2 * PL;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPT;
+    int t = t0 + lane / LPT;
+    const bool live = t < ntiles;
+    if (!live) t = t0;                                   // clamp: recompute a valid tile, discard
+    int g = 0;
+    while (g + 1 < nunits && units[g + 1].tilebase <= t) ++g;
+    const CostUnit &un = units[g];
+    const int local = t - un.tilebase;
+    const int na = un.tr ? un.nj : un.ni, nb = un.tr ? un.ni : un.nj;
+    const int abase = un.rowbase + (un.tr ? un.ni : 0), bbase = un.rowbase + (un.tr ? 0 : un.ni);
+    const int TI = (na + 1) >> 1, TJ = (nb + 3) >> 2;
+    const int ti = local / TJ, tj = local - ti * TJ;
+    int ia[2], jb[4];
+    const float *a[2], *b[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { ia[r] = ti + r * TI; a[r] = rowsbuf + (size_t)(abase + (ia[r] < na ? ia[r] : ti)) * A.ldr; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { jb[c] = tj + c * TJ; b[c] = rowsbuf + (size_t)(bbase + (jb[c] < nb ? jb[c] : tj)) * A.ldr; }
+    float v[8];
+    dist_2x4<PL>(A, a, b, sub, v);
+    // every lane of the tile holds all eight distances; lane `sub` stores cells sub, sub + LPT, ...
+    float mx = 0.f;
+    if (live) {
+        float *tile_p = A.tiles + (int64_t)un.q * A.tile_stride;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if ((c % LPT) == sub) {
+                const int r = c >> 2, cc = c & 3;
+                if (ia[r] < na && jb[cc] < nb) {
+                    const int i = un.i0 + (un.tr ? jb[cc] : ia[r]);
+                    const int j = un.j0 + (un.tr ? ia[r] : jb[cc]);
+                    tile_p[(int64_t)i * un.u2 + j] = v[c];
+                    mx = fmaxf(mx, v[c]);
+                }
+            }
+        }
+        atomicMax(&umax[g], __float_as_uint(mx));        // distances are >= 0: uint order == float order
+    }
+}
+
+struct CostStage {
+    CostUnit units[kGroupMax];
+    unsigned umax[kGroupMax];
+    int nunits, nrows, ntiles, taskctr;
+};
+
+// Small pairs (u1 <= tb and u2 <= tb): producer/consumer ring, one CTA per SM.
+template <int PL>
+__global__ void __launch_bounds__(kCostThreads, 1)
 cost_tiles_kernel(const __grid_constant__ CostArgs A)
 {
-    extern __shared__ __align__(16) float rowsbuf[];
-    __shared__ CostUnit units[kGroupMax];
-    __shared__ unsigned umax[kGroupMax];
-    __shared__ int s_n, s_rows, s_tasks, s_adv;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ CostStage stage[kMaxStages];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = A.stages;
+    const size_t stage_floats = (size_t)A.rcap * A.ldr;
+    float *rows_all = reinterpret_cast<float *>(smem_raw);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCostConsumerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     const int per = (A.npairs + gridDim.x - 1) / gridDim.x;
-    int cur = blockIdx.x * per;
-    const int end = min(A.npairs, cur + per);
-    int64_t tok1, tok2;
-    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const int begin = min(A.npairs, (int)blockIdx.x * per);
+    const int end = min(A.npairs, begin + per);
 
-    while (cur < end) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
+    if (warp == 0) {
+        // ------------------------------ producer ------------------------------
+        int64_t tok1, tok2;
+        { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+        int cur = begin;
+        int it = 0;
+        for (;; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            CostStage &G = stage[s];
+            mbar_wait(&empty_bar[s], ph ^ 1u);                      // stage drained (passes at once the first time round)
+            if (it >= S) {                                          // epilogue of the group that lived here
+                if (lane < G.nunits && G.units[lane].ni > 0) A.maxc[G.units[lane].q] = __uint_as_float(G.umax[lane]);
+            }
+            __syncwarp();
+            if (cur >= end) {
+                // no more work: publish the stop marker once per remaining stage so that every consumer sees it
+                if (lane == 0) { G.nunits = 0; G.nrows = 0; G.ntiles = -1; G.taskctr = 0; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+                break;
+            }
             const int q = cur + lane;
             int u1 = 0, u2 = 0;
             if (q < end) { const int u = A.u12[q]; u1 = u & 0xffff; u2 = u >> 16; }
-            if (u1 > A.tb || u2 > A.tb) { u1 = 0; u2 = 0; }           // handled by the large-pair kernel
+            if (u1 > A.tb || u2 > A.tb) { u1 = 0; u2 = 0; }         // handled by the large-pair kernel
+            const int tr = pick_orientation(u1, u2);
             const int rows = u1 + u2;
-            const int tasks = ((u1 + 1) >> 1) * ((u2 + 1) >> 1) * 2;
-            int rs = rows, ts = tasks;
+            const int tiles = (u1 > 0) ? unit_tiles(u1, u2, tr) : 0;
+            int rs = rows, ts = tiles;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int r = __shfl_up_sync(kFull, rs, o), t2 = __shfl_up_sync(kFull, ts, o);
                 if (lane >= o) { rs += r; ts += t2; }
             }
             const unsigned fits = __ballot_sync(kFull, rs <= A.rcap && q < end);
-            const int cnt = (fits == kFull) ? 32 : (__ffs(~fits) - 1);
+            const int cnt = (fits == kFull) ? 32 : (__ffs(~fits) - 1);   // >= 1: one pair always fits
             if (lane < cnt) {
                 CostUnit un;
                 un.q = q; un.rowbase = rs - rows; un.i0 = 0; un.ni = u1; un.j0 = 0; un.nj = u2; un.u2 = u2;
-                un.taskbase = ts - tasks;
-                int64_t a; int l;
-                doc_span(A.s1, A.p0 + q, a, l); un.o1 = a - tok1;
-                doc_span(A.s2, A.p0 + q, a, l); un.o2 = a - tok2;
-                units[lane] = un;
-                umax[lane] = 0u;
+                un.tilebase = ts - tiles; un.tr = tr; un._pad = 0;
+                int64_t aa; int l;
+                doc_span(A.s1, A.p0 + q, aa, l); un.o1 = aa - tok1;
+                doc_span(A.s2, A.p0 + q, aa, l); un.o2 = aa - tok2;
+                G.units[lane] = un;
+                G.umax[lane] = 0u;
             }
-            if (lane == cnt - 1) { s_n = cnt; s_rows = rs; s_tasks = ts; s_adv = cnt; }
+            const int total_rows = __shfl_sync(kFull, rs, cnt - 1);
+            const int total_tiles = __shfl_sync(kFull, ts, cnt - 1);
+            if (lane == 0) { G.nunits = cnt; G.nrows = total_rows; G.ntiles = total_tiles; G.taskctr = 0; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)total_rows * (uint32_t)A.rowbytes);
+            __syncwarp();
+            float *rowsbuf = rows_all + (size_t)s * stage_floats;
+            for (int rr = lane; rr < total_rows; rr += kWarp) {
+                int g = 0;
+                while (g + 1 < cnt && G.units[g + 1].rowbase <= rr) ++g;
+                const CostUnit &un = G.units[g];
+                const int local = rr - un.rowbase;
+                const int row = local < un.ni ? A.rows1[un.o1 + local] : A.rows2[un.o2 + (local - un.ni)];
+                tma_row_g2s(rowsbuf + (size_t)rr * A.ldr, A.vc.table + (int64_t)row * A.vc.ld, (uint32_t)A.rowbytes, &full_bar[s]);
+            }
+            cur += cnt;
         }
-        __syncthreads();
-        const int n = s_n, total_rows = s_rows, total_tasks = s_tasks;
-        stage_rows(A, units, n, total_rows, rowsbuf);
-        __syncthreads();
-        run_tasks(A, units, n, total_tasks, rowsbuf, umax);
-        __syncthreads();
-        if (threadIdx.x < n) {
-            const CostUnit &un = units[threadIdx.x];
-            if (un.ni > 0) A.maxc[un.q] = __uint_as_float(umax[threadIdx.x]);
+        // drain: the groups still in flight hand their maxima over when their stage empties
+        for (int k = 1; k < S; ++k) {
+            const int it2 = it + k;
+            const int s = it2 % S;
+            if (it2 < S) continue;                                  // that stage was never used
+            const uint32_t ph = (uint32_t)(it2 / S) & 1u;
+            CostStage &G = stage[s];
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            if (lane < G.nunits && G.units[lane].ni > 0) A.maxc[G.units[lane].q] = __uint_as_float(G.umax[lane]);
+            __syncwarp();
         }
-        cur += s_adv;
-        __syncthreads();
+    } else {
+        // ------------------------------ consumers ------------------------------
+        constexpr int TPW = 32 / (2 * PL);
+        for (int it = 0;; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            CostStage &G = stage[s];
+            mbar_wait(&full_bar[s], ph);
+            const int ntiles = G.ntiles;
+            if (ntiles < 0) break;                                  // stop marker
+            const int nunits = G.nunits;
+            const float *rowsbuf = rows_all + (size_t)s * stage_floats;
+            for (;;) {
+                int t0 = 0;
+                if (lane == 0) t0 = atomicAdd(&G.taskctr, TPW);
+                t0 = __shfl_sync(kFull, t0, 0);
+                if (t0 >= ntiles) break;
+                run_tile_batch<PL>(A, G.units, nunits, ntiles, t0, rowsbuf, G.umax);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
     }
 }
 
-// Large pairs (a side with more than tb unique rows): one CTA per pair, tb x tb blocks in turn.
+// Large pairs (a side with more than tb unique rows): one CTA per pair, tb x tb blocks in turn,
+// staged with plain coalesced 128-bit loads (rare path: documents longer than 32 unique tokens).
+template <int PL>
 __global__ void __launch_bounds__(kCostThreads)
 cost_tiles_large_kernel(const __grid_constant__ CostArgs A)
 {
-    extern __shared__ __align__(16) float rowsbuf[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *rowsbuf = reinterpret_cast<float *>(smem_raw);
     __shared__ CostUnit unit;
     __shared__ unsigned umax;
+    constexpr int TPW = 32 / (2 * PL);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const int d4 = A.vc.ld >> 2;
     for (int q = blockIdx.x; q < A.npairs; q += gridDim.x) {
         const int u = A.u12[q];
         const int u1 = u & 0xffff, u2 = u >> 16;
@@ -281,16 +440,25 @@ cost_tiles_large_kernel(const __grid_constant__ CostArgs A)
                 if (threadIdx.x == 0) {
                     CostUnit un;
                     un.q = q; un.rowbase = 0; un.i0 = bi; un.ni = min(A.tb, u1 - bi);
-                    un.j0 = bj; un.nj = min(A.tb, u2 - bj); un.u2 = u2; un.taskbase = 0;
-                    int64_t a; int l;
-                    doc_span(A.s1, A.p0 + q, a, l); un.o1 = a - tok1;
-                    doc_span(A.s2, A.p0 + q, a, l); un.o2 = a - tok2;
+                    un.j0 = bj; un.nj = min(A.tb, u2 - bj); un.u2 = u2; un.tilebase = 0;
+                    un.tr = pick_orientation(un.ni, un.nj); un._pad = 0;
+                    int64_t aa; int l;
+                    doc_span(A.s1, A.p0 + q, aa, l); un.o1 = aa - tok1;
+                    doc_span(A.s2, A.p0 + q, aa, l); un.o2 = aa - tok2;
                     unit = un;
                 }
                 __syncthreads();
-                stage_rows(A, &unit, 1, unit.ni + unit.nj, rowsbuf);
+                const int nrows = unit.ni + unit.nj;
+                for (int rr = warp; rr < nrows; rr += nwarps) {
+                    const int row = rr < unit.ni ? A.rows1[unit.o1 + unit.i0 + rr] : A.rows2[unit.o2 + unit.j0 + (rr - unit.ni)];
+                    const float4 *src = reinterpret_cast<const float4 *>(A.vc.table + (int64_t)row * A.vc.ld);
+                    float4 *dst = reinterpret_cast<float4 *>(rowsbuf + (size_t)rr * A.ldr);
+                    for (int k = lane; k < d4; k += kWarp) dst[k] = __ldg(src + k);
+                }
                 __syncthreads();
-                run_tasks(A, &unit, 1, ((unit.ni + 1) >> 1) * ((unit.nj + 1) >> 1) * 2, rowsbuf, &umax);
+                const int ntiles = unit_tiles(unit.ni, unit.nj, unit.tr);
+                for (int t0 = warp * TPW; t0 < ntiles; t0 += nwarps * TPW)
+                    run_tile_batch<PL>(A, &unit, 1, ntiles, t0, rowsbuf, &umax);
             }
         __syncthreads();
         if (threadIdx.x == 0) A.maxc[q] = __uint_as_float(umax);

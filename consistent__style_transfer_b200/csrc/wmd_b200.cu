@@ -182,37 +182,64 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         CK(cudaGetLastError());
     }
     // ---- K2
-    int tb;
     {
         CostArgs A;
         A.vc = vc; A.plan = E->plan; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
-        int ldr4 = (E->d + 3) / 4;
+        int ldr4 = E->ld / 4;
         if ((ldr4 & 1) == 0) ldr4++;
         A.ldr = ldr4 * 4;
-        const size_t rowbytes = (size_t)A.ldr * 4;
-        size_t budget = 96 * 1024;
-        int rcap = (int)(budget / rowbytes);
-        if (rcap < 16) { budget = std::min<size_t>(E->smem_optin - 4096, 200 * 1024); rcap = (int)(budget / rowbytes); }
-        if (rcap < 2) return fail(WMD_EINVAL, "embedding width %d does not fit the shared-memory staging buffer", E->d);
-        rcap = std::min(rcap, 512);
-        tb = std::min(32, rcap / 2);
-        A.tb = tb; A.rcap = rcap;
+        A.rowbytes = E->ld * 4;
+        A.negzero2 = 0x8000000080000000ull;
+        A._pad = 0;
+        const size_t srow = (size_t)A.ldr * 4;                       // bytes per staged row
+        const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 12 * 1024;   // static stage records + barriers
+        int tb = std::min(32, ML);
+        while (tb > 1 && (size_t)2 * (2 * tb) * srow > budget) tb >>= 1;
+        if ((size_t)2 * (2 * tb) * srow > budget) return fail(WMD_EINVAL, "embedding width %d does not fit the shared-memory ring", E->d);
+        int rcap = std::max(2 * tb, (int)((48 * 1024) / srow));
+        rcap = std::min(rcap, 1024);
+        int stages = (int)std::min<size_t>(kMaxStages, budget / ((size_t)rcap * srow));
+        if (stages < 2) { rcap = 2 * tb; stages = (int)std::min<size_t>(kMaxStages, budget / ((size_t)rcap * srow)); }
+        A.tb = tb; A.rcap = rcap; A.stages = stages;
+        const SumPlan &pl = E->plan;
+        int PL = 1;
+        bool minlen = true;
+        for (int o = 0; o < pl.nops; ++o) minlen = minlen && pl.len[o] >= 8;
+        if (minlen && pl.nops == 4 && pl.adds[0] == 0 && pl.adds[1] == 1 && pl.adds[2] == 0 && pl.adds[3] == 2) PL = 4;
+        else if (minlen && pl.nops == 2 && pl.adds[0] == 0 && pl.adds[1] == 1) PL = 2;
+        A.pl = PL;
         A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
         A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride; A.maxc = W.maxc.as<float>();
-        const size_t smem = (size_t)rcap * rowbytes;
-        CK(cudaFuncSetAttribute(cost_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = (size_t)stages * rcap * srow;
         {
-            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count * 2);
+            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
             Prof pr(E, WMD_K_COST, st);
-            cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
+            if (PL == 4) {
+                CK(cudaFuncSetAttribute(cost_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cost_tiles_kernel<4><<<grid, kCostThreads, smem, st>>>(A);
+            } else if (PL == 2) {
+                CK(cudaFuncSetAttribute(cost_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cost_tiles_kernel<2><<<grid, kCostThreads, smem, st>>>(A);
+            } else {
+                CK(cudaFuncSetAttribute(cost_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cost_tiles_kernel<1><<<grid, kCostThreads, smem, st>>>(A);
+            }
             CK(cudaGetLastError());
         }
         if (ML > tb) {
-            const size_t smem_l = (size_t)2 * tb * rowbytes;
-            CK(cudaFuncSetAttribute(cost_tiles_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            const size_t smem_l = (size_t)2 * tb * srow;
             const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count * 2);
             Prof pr(E, WMD_K_COST, st);
-            cost_tiles_large_kernel<<<grid, kCostThreads, smem_l, st>>>(A);
+            if (PL == 4) {
+                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                cost_tiles_large_kernel<4><<<grid, kCostThreads, smem_l, st>>>(A);
+            } else if (PL == 2) {
+                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                cost_tiles_large_kernel<2><<<grid, kCostThreads, smem_l, st>>>(A);
+            } else {
+                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                cost_tiles_large_kernel<1><<<grid, kCostThreads, smem_l, st>>>(A);
+            }
             CK(cudaGetLastError());
         }
     }
