@@ -25,7 +25,7 @@
 
 namespace wmd {
 
-constexpr int kCostConsumerWarps = 8;
+constexpr int kCostConsumerWarps = 16;
 constexpr int kCostThreads = 32 * (1 + kCostConsumerWarps);
 constexpr int kGroupMax = 32;        // pairs per staged group
 constexpr int kPlanDepth = 8;
@@ -115,22 +115,22 @@ __device__ __forceinline__ float quad_sum(const Q4 a)
     return __fadd_rn(__fadd_rn(lo_f(a.lo), hi_f(a.lo)), __fadd_rn(lo_f(a.hi), hi_f(a.hi)));
 }
 
-// One leaf block [start, start+len) of numpy's pairwise sum for the 2x4 cells (a_r, b_c).
-// half selects accumulators r[0..3] or r[4..7]; the two lanes meet with one shuffle.
+// One leaf block [start, start+len) of numpy's pairwise sum for the 2x4 cells (a_r, b_c), c = 4r + cc.
+// half selects accumulators r[0..3] or r[4..7].  The two lanes of a pair meet in a reduce-scatter:
+// afterwards lane `half` holds the four cells c = 2j + half (j = 0..3) in res[j], tail included.
 __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float *const (&b)[4], int start, int len,
-                                         int half, f32x2 nz, float (&res)[8])
+                                         int half, f32x2 nz, float (&res)[4])
 {
-    if (len < 8) {                                     // numpy: plain sequential loop
+    const float *bk[2] = { half ? b[1] : b[0], half ? b[3] : b[2] };      // columns of the kept cells: half, 2 + half
+    if (len < 8) {                                     // numpy: plain sequential loop (only when d < 8)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) res[c] = 0.f;
+        for (int j = 0; j < 4; ++j) res[j] = 0.f;
         for (int e = start; e < start + len; ++e) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float t = __fsub_rn(a[r][e], b[c][e]);
-                    res[r * 4 + c] = __fadd_rn(res[r * 4 + c], __fmul_rn(t, t));
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float t = __fsub_rn(a[j >> 1][e], bk[j & 1][e]);
+                res[j] = __fadd_rn(res[j], __fmul_rn(t, t));
+            }
         }
         return;
     }
@@ -168,59 +168,69 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
             }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float p = quad_sum(acc[c]);
-        const float o = __shfl_xor_sync(kFull, p, 1);
-        res[c] = half ? __fadd_rn(o, p) : __fadd_rn(p, o);       // (r0+r1+r2+r3) + (r4+..+r7)
+    for (int j = 0; j < 4; ++j) {
+        const float p0 = quad_sum(acc[2 * j]), p1 = quad_sum(acc[2 * j + 1]);
+        const float mine = half ? p1 : p0, theirs = half ? p0 : p1;
+        const float o = __shfl_xor_sync(kFull, theirs, 1);
+        res[j] = __fadd_rn(mine, o);                               // (r0+r1+r2+r3) + (r4+..+r7); fadd commutes
     }
-    for (int t = eend; t < start + len; ++t) {                    // the len % 8 tail, sequential
+    for (int t = eend; t < start + len; ++t) {                     // the len % 8 tail, sequential, kept cells only
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float s = __fsub_rn(a[r][t], b[c][t]);
-                res[r * 4 + c] = __fadd_rn(res[r * 4 + c], __fmul_rn(s, s));
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float s = __fsub_rn(a[j >> 1][t], bk[j & 1][t]);
+            res[j] = __fadd_rn(res[j], __fmul_rn(s, s));
+        }
     }
 }
 
-// The eight distances of one tile task. PL = 1: the lane pair walks the whole postfix program;
-// PL = 2 / 4: leaf l of a balanced tree is summed by lane pair l and the tree is closed by shuffles.
+// Distances of one tile task.  PL = 1: the lane pair walks the whole postfix program and each lane
+// ends with the four cells c = 2j + half.  PL = 2 / 4: leaf l of a balanced tree is summed by lane
+// pair l and the tree is closed by further reduce-scatter steps, leaving 2 / 1 cells per lane.
+// out[k] is cell cell0 + k * cstep of the tile.
 template <int PL>
 __device__ __forceinline__ void dist_2x4(const CostArgs &A, const float *const (&a)[2], const float *const (&b)[4],
-                                         int sub, float (&out)[8])
+                                         int sub, float (&out)[4 / PL], int &cell0, int &cstep)
 {
     const int half = sub & 1;
     if (PL == 1) {
-        float st[kPlanDepth][8];
+        float st[kPlanDepth][4];
         int sp = 0;
         for (int o = 0; o < A.plan.nops; ++o) {
-            float r[8];
+            float r[4];
             leaf_2x4(a, b, A.plan.start[o], A.plan.len[o], half, A.negzero2, r);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) st[sp][c] = r[c];
+            for (int c = 0; c < 4; ++c) st[sp][c] = r[c];
             ++sp;
             for (int k = 0; k < A.plan.adds[o]; ++k) {
                 --sp;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) st[sp - 1][c] = __fadd_rn(st[sp - 1][c], st[sp][c]);
+                for (int c = 0; c < 4; ++c) st[sp - 1][c] = __fadd_rn(st[sp - 1][c], st[sp][c]);
             }
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = __fsqrt_rn(st[0][c]);
+        for (int c = 0; c < 4 / PL; ++c) out[c] = __fsqrt_rn(st[0][c]);
+        cell0 = half; cstep = 2;
     } else {
-        const int l = sub >> 1;
-        float r[8];
+        const int l = sub >> 1, l0 = l & 1;
+        float r[4];
         leaf_2x4(a, b, A.plan.start[l], A.plan.len[l], half, A.negzero2, r);
+        float k2[2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float o = __shfl_xor_sync(kFull, r[c], 2);
-            r[c] = (l & 1) ? __fadd_rn(o, r[c]) : __fadd_rn(r[c], o);          // L0+L1, L2+L3
-            if (PL == 4) {
-                o = __shfl_xor_sync(kFull, r[c], 4);
-                r[c] = (l & 2) ? __fadd_rn(o, r[c]) : __fadd_rn(r[c], o);      // (L0+L1)+(L2+L3)
-            }
-            out[c] = __fsqrt_rn(r[c]);
+        for (int m = 0; m < 2; ++m) {                              // L0 + L1 (and L2 + L3): keep cells with bit 1 == l0
+            const float mine = l0 ? r[2 * m + 1] : r[2 * m], theirs = l0 ? r[2 * m] : r[2 * m + 1];
+            const float o = __shfl_xor_sync(kFull, theirs, 2);
+            k2[m] = __fadd_rn(mine, o);
+        }
+        if (PL == 2) {
+#pragma unroll
+            for (int m = 0; m < 4 / PL; ++m) out[m] = __fsqrt_rn(k2[m & 1]);
+            cell0 = 2 * l0 + half; cstep = 4;
+        } else {
+            const int l1 = l >> 1;                                 // (L0+L1) + (L2+L3): keep the cell with bit 2 == l1
+            const float mine = l1 ? k2[1] : k2[0], theirs = l1 ? k2[0] : k2[1];
+            const float o = __shfl_xor_sync(kFull, theirs, 4);
+            out[0] = __fsqrt_rn(__fadd_rn(mine, o));
+            cell0 = sub; cstep = 8;
         }
     }
 }
@@ -262,22 +272,23 @@ __device__ __forceinline__ void run_tile_batch(const CostArgs &A, const CostUnit
     for (int r = 0; r < 2; ++r) { ia[r] = ti + r * TI; a[r] = rowsbuf + (size_t)(abase + (ia[r] < na ? ia[r] : ti)) * A.ldr; }
 #pragma unroll
     for (int c = 0; c < 4; ++c) { jb[c] = tj + c * TJ; b[c] = rowsbuf + (size_t)(bbase + (jb[c] < nb ? jb[c] : tj)) * A.ldr; }
-    float v[8];
-    dist_2x4<PL>(A, a, b, sub, v);
-    // every lane of the tile holds all eight distances; lane `sub` stores cells sub, sub + LPT, ...
-    float mx = 0.f;
+    float v[4 / PL];
+    int cell0, cstep;
+    dist_2x4<PL>(A, a, b, sub, v, cell0, cstep);
     if (live) {
         float *tile_p = A.tiles + (int64_t)un.q * A.tile_stride;
+        float mx = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if ((c % LPT) == sub) {
-                const int r = c >> 2, cc = c & 3;
-                if (ia[r] < na && jb[cc] < nb) {
-                    const int i = un.i0 + (un.tr ? jb[cc] : ia[r]);
-                    const int j = un.j0 + (un.tr ? ia[r] : jb[cc]);
-                    tile_p[(int64_t)i * un.u2 + j] = v[c];
-                    mx = fmaxf(mx, v[c]);
-                }
+        for (int k = 0; k < 4 / PL; ++k) {
+            const int c = cell0 + k * cstep;
+            const int r = c >> 2, cc = c & 3;
+            const int iar = r ? ia[1] : ia[0];
+            const int jbc = cc == 0 ? jb[0] : (cc == 1 ? jb[1] : (cc == 2 ? jb[2] : jb[3]));
+            if (iar < na && jbc < nb) {
+                const int i = un.i0 + (un.tr ? jbc : iar);
+                const int j = un.j0 + (un.tr ? iar : jbc);
+                tile_p[(int64_t)i * un.u2 + j] = v[k];
+                mx = fmaxf(mx, v[k]);
             }
         }
         atomicMax(&umax[g], __float_as_uint(mx));        // distances are >= 0: uint order == float order
