@@ -186,6 +186,21 @@ class WMDEngine:
                                                 B, int(pad_id), MODE_PYEMD, out.data_ptr(), status.data_ptr(), stream))
         return out, status
 
+    def wmd_pairs_torch(self, ids1, off1, ids2, off2):
+        """Host CSR (numpy) in, torch CUDA tensors (float64 scores, int32 status) out: the shape
+        ``sharding.wmd_pairs_sharded`` wants as its ``score_fn`` (scores stay on the device for the
+        NCCL gather)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
+        off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
+        B = off1.shape[0] - 1
+        if B == 0:
+            return torch.empty(0, dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
+        ml1, ml2 = int(np.diff(off1).max()), int(np.diff(off2).max())
+        t = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)
+        return self.wmd_pairs_cuda(t(ids1), t(off1), t(ids2), t(off2), ml1, ml2)
+
     # -- instrumentation --------------------------------------------------------------------
     def set_profiling(self, enabled: bool):
         _lib.check(self._L.wmd_set_profiling(self._handle(), int(bool(enabled))))

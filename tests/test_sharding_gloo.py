@@ -1,0 +1,80 @@
+"""world_size-2 (and 3) gloo runs of the multi-rank host logic on CPU: cost-balanced contiguous
+partition, per-rank scoring of disjoint slices, one gather of the scores in input order.  There is
+no GPU here, so the per-rank scorer is the oracle -- what is under test is the sharding layer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from consistent__style_transfer_b200 import sharding, workload
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, B, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import wmd_oracle
+        table = workload.make_table(300, 16, seed=1)
+        ids1, off1, ids2, off2 = workload.make_pairs(B, "book", "independent", V=300, seed=4)
+        calls = []
+
+        def score(a1, o1, a2, o2):
+            calls.append(len(o1) - 1)
+            out, st = wmd_oracle.batch_wmd(table, a1, o1, a2, o2)
+            return torch.from_numpy(out), torch.from_numpy(st)
+
+        out, st, (lo, hi) = sharding.wmd_pairs_sharded(score, ids1, off1, ids2, off2)
+        q.put((rank, lo, hi, calls[0], out.numpy().tobytes(), st.numpy().tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,B", [(2, 257), (3, 100), (2, 1)])
+def test_sharded_scores_equal_single_rank(oracle, world, B):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    table = workload.make_table(300, 16, seed=1)
+    ids1, off1, ids2, off2 = workload.make_pairs(B, "book", "independent", V=300, seed=4)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2)
+    covered = 0
+    for rank, lo, hi, ncalls, ob, sb in res:
+        assert ncalls == hi - lo                       # each rank scored only its own slice
+        assert lo == covered
+        covered = hi
+        assert ob == want.tobytes() and sb == wst.tobytes()   # every rank holds all scores, input order
+    assert covered == B
+
+
+def test_partition_is_balanced_and_total():
+    rng = np.random.default_rng(0)
+    cost = rng.integers(1, 500, size=10_000).astype(np.float64)
+    for world in (1, 2, 4, 8):
+        b = sharding.partition(cost, world)
+        assert b[0] == 0 and b[-1] == len(cost) and np.all(np.diff(b) >= 0)
+        per = [cost[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert max(per) <= cost.sum() / world + cost.max()
+    assert list(sharding.partition(np.zeros(0), 4)) == [0, 0, 0, 0, 0]
+    assert list(sharding.row_blocks(10, 4)) == [0, 2, 5, 7, 10]
+
+
+def test_csr_slice_rebases_offsets():
+    ids, off = workload.to_csr([[1, 2], [], [3], [4, 5, 6]])
+    a, o = sharding.csr_slice(ids, off, 1, 4)
+    assert list(a) == [3, 4, 5, 6] and list(o) == [0, 0, 1, 4]
