@@ -8,76 +8,92 @@
 // FLOAT_pairwise_sum order -- eight strided accumulators per leaf block, leaves combined by
 // the recursion tree that SumPlan flattens.
 //
-// Structure (sm_100a).  One persistent CTA per SM runs a producer/consumer ring:
-//   * warp 0 (producer) walks its slice of pairs, packs consecutive pairs into a stage
-//     ("group"), and gathers their table rows HBM/L2 -> shared memory with 1-D TMA bulk copies
-//     (cp.async.bulk ... mbarrier::complete_tx), one copy per row, each row fetched once per pair;
-//   * the consumer warps wait on the stage's "full" mbarrier, pull tile tasks from a shared
-//     counter, and release the stage through its "empty" mbarrier; they never barrier with each
-//     other, so a warp that runs out of tiles in one stage starts on the next.
-// A tile task is a 2x4 block of cells owned by 2*PL adjacent lanes: lane (leaf l, half h) keeps
-// the accumulator quads r[4h..4h+3] of leaf block l for all eight cells, i.e. 6 LDS.128 per 96
-// float operations, which balances the 128 B/clk shared-memory port against the FP32 pipe.
+// Structure (sm_100a), v4: every warp is an autonomous software pipeline; there is no producer
+// warp and no CTA-wide barrier (v3 spent > 50 % of its samples spinning on the producer).
+//   * a warp claims pairs from a global counter, cuts them into "units" (up to 4 blocks of
+//     consecutive pairs, <= 16 tile tasks, <= 24 table rows) and streams the unit's rows
+//     L2 -> shared memory in CHUNKS of a few dozen floats per row with 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP), one copy per row per chunk,
+//     double-buffered per warp: chunk k+1 (or the first chunk of the next unit) is in flight
+//     while chunk k is being summed.  A chunk never straddles a leaf of numpy's recursion.
+//   * a tile task is a 2x4 block of cells owned by a lane pair: lane `half` keeps the accumulator
+//     quad r[4h..4h+3] of the current leaf for all eight cells in registers ACROSS chunks, i.e.
+//     6 LDS.128 per 96 float operations, which balances the 128 B/clk shared-memory port against
+//     the FP32 pipe; leaf sums meet in a reduce-scatter (4 cells per lane) and the recursion tree
+//     is a 4-deep register stack.
 // The float math is issued as packed FADD2/FFMA2 (sub.f32x2, fma.f32x2 with a -0.0 addend that
 // ptxas cannot see, add.f32x2): identical IEEE roundings, half the issue slots.
+// Shared memory per warp is 2 x 24 rows x chunk pitch (~8 KB), so 16 warps fit in ~130 KB and the
+// latency-bound solver (K3) can be co-resident on the same SM from the engine's other stream.
 #pragma once
 #include "common.cuh"
 
 namespace wmd {
 
-constexpr int kCostConsumerWarps = 16;
-constexpr int kCostThreads = 32 * (1 + kCostConsumerWarps);
-constexpr int kGroupMax = 32;        // pairs per staged group
-constexpr int kPlanDepth = 8;
-constexpr int kMaxStages = 4;
+constexpr int kCostWarps = 4;             // warps per CTA (each one autonomous)
+constexpr int kCostThreads = 32 * kCostWarps;
+constexpr int kUnitSubs = 4;              // blocks (of consecutive pairs) per unit
+constexpr int kUnitRows = 24;             // staged rows per unit
+constexpr int kUnitTiles = 16;            // tile tasks per unit = lane pairs per warp
+constexpr int kStackDepth = 4;            // register stack of leaf sums (d <= 1024)
+constexpr int kMaxChunks = 96;
+constexpr int kClaim = 8;                 // pairs claimed per atomic
+
+struct CostChunk {
+    uint16_t foff;                        // first float of the chunk inside a table row (multiple of 8)
+    uint16_t bytes;                       // bytes copied per row (multiple of 16)
+    uint16_t niter;                       // 8-float iterations (0 for a sequential leaf)
+    uint8_t tail;                         // floats after the 8-wide part (only on the last chunk of a leaf)
+    uint8_t flags;                        // 1 = first chunk of a leaf, 2 = last chunk, 4 = sequential leaf (len < 8)
+    uint8_t adds;                         // stack pops after the leaf (only on its last chunk)
+    uint8_t _p[3];
+};
 
 struct CostArgs {
     Vocab vc;
-    SumPlan plan;
     DocSide s1, s2;                  // only .off / .L are used (document slots)
-    int64_t p0;                      // first pair of this chunk
-    int32_t npairs;                  // pairs in this chunk
-    int32_t tb;                      // max rows per side of a staged unit (<= 32)
-    int32_t rcap;                    // row capacity of one stage
-    int32_t ldr;                     // floats between staged rows (multiple of 4)
-    int32_t stages;                  // ring depth (2..kMaxStages)
-    int32_t pl;                      // leaf blocks processed in parallel by one tile (1, 2 or 4)
-    int32_t rowbytes;                // bytes copied per row (ld * 4, multiple of 16)
+    int64_t p0;                      // first pair of this chunk of pairs
+    int32_t npairs;                  // pairs in this launch
+    int32_t nchunks;
+    int32_t pitch;                   // bytes between staged rows (== 32 mod 64: conflict-free LDS.128)
     int32_t _pad;
     unsigned long long negzero2;     // 0x8000000080000000: (-0.0f, -0.0f), opaque to ptxas
     const int32_t *rows1, *rows2;    // from K1
     const int32_t *u12;
     float *tiles;                    // [npairs, tile_stride]
     int64_t tile_stride;
-    float *maxc;                     // [npairs]
+    unsigned int *maxc;              // [npairs] float bits, zeroed by the host before the launch
+    unsigned int *counter;           // work-claim counter, zeroed by the host
+    CostChunk chunks[kMaxChunks];
 };
 
-struct CostUnit {
-    int32_t q;                       // pair (chunk-local)
-    int32_t rowbase;                 // first staged row
-    int32_t i0, ni, j0, nj;          // sub-block of the pair's tile (doc1 rows x doc2 rows)
+struct CostSub {
+    int32_t q;                       // pair (launch-local)
+    int32_t i0, ni, j0, nj;          // block of the pair's tile (doc1 rows x doc2 rows)
     int32_t u2;                      // tile row pitch
-    int32_t tilebase;                // first tile task of the unit inside its group
     int32_t tr;                      // 1: the 2-side of the 2x4 tile runs along doc2
+    int32_t tilebase;                // first tile task of the block inside its unit
+    int32_t rowbase;                 // first staged row
     int32_t _pad;
     int64_t o1, o2;                  // token-slot offsets of the pair
 };
 
+struct CostWarpState {
+    CostSub subs[2][kUnitSubs];
+    unsigned long long bar[2];
+};
+
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
     const long long t0 = clock64();
@@ -89,10 +105,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (clock64() - t0 > (1ll << 33)) __trap();       // ~4 s: a protocol bug must fault, never hang the GPU
     }
 }
-__device__ __forceinline__ void tma_row_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void tma_row_g2s(uint32_t dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 typedef unsigned long long f32x2;
@@ -115,30 +135,41 @@ __device__ __forceinline__ float quad_sum(const Q4 a)
     return __fadd_rn(__fadd_rn(lo_f(a.lo), hi_f(a.lo)), __fadd_rn(lo_f(a.hi), hi_f(a.hi)));
 }
 
-// One leaf block [start, start+len) of numpy's pairwise sum for the 2x4 cells (a_r, b_c), c = 4r + cc.
-// half selects accumulators r[0..3] or r[4..7].  The two lanes of a pair meet in a reduce-scatter:
-// afterwards lane `half` holds the four cells c = 2j + half (j = 0..3) in res[j], tail included.
-__device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float *const (&b)[4], int start, int len,
-                                         int half, f32x2 nz, float (&res)[4])
+__device__ __forceinline__ int unit_tiles(int ni, int nj, int tr)
+{
+    const int na = tr ? nj : ni, nb = tr ? ni : nj;
+    return ((na + 1) >> 1) * ((nb + 3) >> 2);
+}
+__device__ __forceinline__ int pick_orientation(int ni, int nj)
+{
+    const int p0 = ((ni + 1) >> 1) * ((nj + 3) >> 2);              // tile tasks, 2-side along doc1
+    const int p1 = ((nj + 1) >> 1) * ((ni + 3) >> 2);
+    return p1 < p0 ? 1 : 0;
+}
+
+// One chunk of a leaf for the 2x4 cells (a_r, b_c), c = 4r + cc.  `half` selects accumulators
+// r[0..3] or r[4..7].  acc persists in registers from the first chunk of a leaf to its last; on the
+// last chunk the two lanes of a pair meet in a reduce-scatter and lane `half` receives the four
+// cells c = 2j + half (j = 0..3) in res[j], tail included.  Returns true when res is valid.
+__device__ __forceinline__ bool chunk_2x4(const CostChunk ck, const float *const (&a)[2], const float *const (&b)[4],
+                                          int half, f32x2 nz, Q4 (&acc)[8], float (&res)[4])
 {
     const float *bk[2] = { half ? b[1] : b[0], half ? b[3] : b[2] };      // columns of the kept cells: half, 2 + half
-    if (len < 8) {                                     // numpy: plain sequential loop (only when d < 8)
+    if (ck.flags & 4) {                                // numpy: plain sequential loop (only when d < 8)
 #pragma unroll
         for (int j = 0; j < 4; ++j) res[j] = 0.f;
-        for (int e = start; e < start + len; ++e) {
+        for (int e = 0; e < ck.tail; ++e) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float t = __fsub_rn(a[j >> 1][e], bk[j & 1][e]);
                 res[j] = __fadd_rn(res[j], __fmul_rn(t, t));
             }
         }
-        return;
+        return true;
     }
-    const int nfull = len - (len & 7);
-    int e = start + 4 * half;
-    const int eend = start + nfull;
-    Q4 acc[8];
-    {
+    int e = 4 * half;
+    const int eend = 8 * ck.niter;
+    if (ck.flags & 1) {
         Q4 x[2], y[4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
@@ -151,9 +182,10 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
                 acc[r * 4 + c].lo = sq2(sub2(x[r].lo, y[c].lo), nz);
                 acc[r * 4 + c].hi = sq2(sub2(x[r].hi, y[c].hi), nz);
             }
+        e += 8;
     }
 #pragma unroll 2
-    for (e += 8; e < eend; e += 8) {
+    for (; e < eend; e += 8) {
         Q4 x[2], y[4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
@@ -167,6 +199,7 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
                 acc[r * 4 + c].hi = add2(acc[r * 4 + c].hi, sq2(sub2(x[r].hi, y[c].hi), nz));
             }
     }
+    if (!(ck.flags & 2)) return false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float p0 = quad_sum(acc[2 * j]), p1 = quad_sum(acc[2 * j + 1]);
@@ -174,311 +207,225 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
         const float o = __shfl_xor_sync(kFull, theirs, 1);
         res[j] = __fadd_rn(mine, o);                               // (r0+r1+r2+r3) + (r4+..+r7); fadd commutes
     }
-    for (int t = eend; t < start + len; ++t) {                     // the len % 8 tail, sequential, kept cells only
+    for (int t = eend; t < eend + ck.tail; ++t) {                  // the len % 8 tail, sequential, kept cells only
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float s = __fsub_rn(a[j >> 1][t], bk[j & 1][t]);
             res[j] = __fadd_rn(res[j], __fmul_rn(s, s));
         }
     }
+    return true;
 }
 
-// Distances of one tile task.  PL = 1: the lane pair walks the whole postfix program and each lane
-// ends with the four cells c = 2j + half.  PL = 2 / 4: leaf l of a balanced tree is summed by lane
-// pair l and the tree is closed by further reduce-scatter steps, leaving 2 / 1 cells per lane.
-// out[k] is cell cell0 + k * cstep of the tile.
-template <int PL>
-__device__ __forceinline__ void dist_2x4(const CostArgs &A, const float *const (&a)[2], const float *const (&b)[4],
-                                         int sub, float (&out)[4 / PL], int &cell0, int &cstep)
+// Splits a pair's u1 x u2 tile into nbi x nbj blocks of at most kUnitTiles tile tasks and
+// kUnitRows rows each (balanced block sizes; the fewest blocks that fit).  Warp-uniform scalar code.
+__device__ __forceinline__ void choose_blocks(int u1, int u2, int &BI, int &BJ, int &nbi, int &nbj)
 {
-    const int half = sub & 1;
-    if (PL == 1) {
-        float st[kPlanDepth][4];
-        int sp = 0;
-        for (int o = 0; o < A.plan.nops; ++o) {
-            float r[4];
-            leaf_2x4(a, b, A.plan.start[o], A.plan.len[o], half, A.negzero2, r);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) st[sp][c] = r[c];
-            ++sp;
-            for (int k = 0; k < A.plan.adds[o]; ++k) {
-                --sp;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) st[sp - 1][c] = __fadd_rn(st[sp - 1][c], st[sp][c]);
+    int best = 0x7fffffff;
+    BI = 1; BJ = 1; nbi = u1; nbj = u2;
+    for (int a = 1; a <= u1; ++a) {
+        if (a >= best) break;
+        const int bi = (u1 + a - 1) / a;
+        for (int b = 1; b <= u2; ++b) {
+            if (a * b >= best) break;
+            const int bj = (u2 + b - 1) / b;
+            if (bi + bj <= kUnitRows && unit_tiles(bi, bj, pick_orientation(bi, bj)) <= kUnitTiles) {
+                best = a * b; BI = bi; BJ = bj; nbi = a; nbj = b;
+                break;
             }
         }
-#pragma unroll
-        for (int c = 0; c < 4 / PL; ++c) out[c] = __fsqrt_rn(st[0][c]);
-        cell0 = half; cstep = 2;
-    } else {
-        const int l = sub >> 1, l0 = l & 1;
-        float r[4];
-        leaf_2x4(a, b, A.plan.start[l], A.plan.len[l], half, A.negzero2, r);
-        float k2[2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {                              // L0 + L1 (and L2 + L3): keep cells with bit 1 == l0
-            const float mine = l0 ? r[2 * m + 1] : r[2 * m], theirs = l0 ? r[2 * m] : r[2 * m + 1];
-            const float o = __shfl_xor_sync(kFull, theirs, 2);
-            k2[m] = __fadd_rn(mine, o);
-        }
-        if (PL == 2) {
-#pragma unroll
-            for (int m = 0; m < 4 / PL; ++m) out[m] = __fsqrt_rn(k2[m & 1]);
-            cell0 = 2 * l0 + half; cstep = 4;
-        } else {
-            const int l1 = l >> 1;                                 // (L0+L1) + (L2+L3): keep the cell with bit 2 == l1
-            const float mine = l1 ? k2[1] : k2[0], theirs = l1 ? k2[0] : k2[1];
-            const float o = __shfl_xor_sync(kFull, theirs, 4);
-            out[0] = __fsqrt_rn(__fadd_rn(mine, o));
-            cell0 = sub; cstep = 8;
-        }
+        if (bi == 1) break;
     }
 }
 
-__device__ __forceinline__ int unit_tiles(int ni, int nj, int tr)
-{
-    const int na = tr ? nj : ni, nb = tr ? ni : nj;
-    return ((na + 1) >> 1) * ((nb + 3) >> 2);
-}
-__device__ __forceinline__ int pick_orientation(int ni, int nj)
-{
-    const int p0 = ((ni + 1) >> 1) * 2 * ((nj + 3) >> 2) * 4;      // padded cells, 2-side along doc1
-    const int p1 = ((nj + 1) >> 1) * 2 * ((ni + 3) >> 2) * 4;
-    return p1 < p0 ? 1 : 0;
-}
-
-// Executes one warp-wide batch of tile tasks [t0, t0 + 32 / (2 PL)) of a group.
-template <int PL>
-__device__ __forceinline__ void run_tile_batch(const CostArgs &A, const CostUnit *units, int nunits, int ntiles, int t0,
-                                               const float *rowsbuf, unsigned *umax)
-{
-    constexpr int LPT = 2 * PL;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % LPT;
-    int t = t0 + lane / LPT;
-    const bool live = t < ntiles;
-    if (!live) t = t0;                                   // clamp: recompute a valid tile, discard
-    int g = 0;
-    while (g + 1 < nunits && units[g + 1].tilebase <= t) ++g;
-    const CostUnit &un = units[g];
-    const int local = t - un.tilebase;
-    const int na = un.tr ? un.nj : un.ni, nb = un.tr ? un.ni : un.nj;
-    const int abase = un.rowbase + (un.tr ? un.ni : 0), bbase = un.rowbase + (un.tr ? 0 : un.ni);
-    const int TI = (na + 1) >> 1, TJ = (nb + 3) >> 2;
-    const int ti = local / TJ, tj = local - ti * TJ;
-    int ia[2], jb[4];
-    const float *a[2], *b[4];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) { ia[r] = ti + r * TI; a[r] = rowsbuf + (size_t)(abase + (ia[r] < na ? ia[r] : ti)) * A.ldr; }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { jb[c] = tj + c * TJ; b[c] = rowsbuf + (size_t)(bbase + (jb[c] < nb ? jb[c] : tj)) * A.ldr; }
-    float v[4 / PL];
-    int cell0, cstep;
-    dist_2x4<PL>(A, a, b, sub, v, cell0, cstep);
-    if (live) {
-        float *tile_p = A.tiles + (int64_t)un.q * A.tile_stride;
-        float mx = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4 / PL; ++k) {
-            const int c = cell0 + k * cstep;
-            const int r = c >> 2, cc = c & 3;
-            const int iar = r ? ia[1] : ia[0];
-            const int jbc = cc == 0 ? jb[0] : (cc == 1 ? jb[1] : (cc == 2 ? jb[2] : jb[3]));
-            if (iar < na && jbc < nb) {
-                const int i = un.i0 + (un.tr ? jbc : iar);
-                const int j = un.j0 + (un.tr ? iar : jbc);
-                tile_p[(int64_t)i * un.u2 + j] = v[k];
-                mx = fmaxf(mx, v[k]);
-            }
-        }
-        atomicMax(&umax[g], __float_as_uint(mx));        // distances are >= 0: uint order == float order
-    }
-}
-
-struct CostStage {
-    CostUnit units[kGroupMax];
-    unsigned umax[kGroupMax];
-    int nunits, nrows, ntiles, taskctr;
-};
-
-// Small pairs (u1 <= tb and u2 <= tb): producer/consumer ring, one CTA per SM.
-template <int PL>
-__global__ void __launch_bounds__(kCostThreads, 1)
+__global__ void __launch_bounds__(kCostThreads)
 cost_tiles_kernel(const __grid_constant__ CostArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ CostStage stage[kMaxStages];
-    __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ CostWarpState wstate[kCostWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int S = A.stages;
-    const size_t stage_floats = (size_t)A.rcap * A.ldr;
-    float *rows_all = reinterpret_cast<float *>(smem_raw);
+    const int half = lane & 1, lp = lane >> 1;
+    CostWarpState &W = wstate[warp];
+    const uint32_t bufbytes = (uint32_t)kUnitRows * (uint32_t)A.pitch;
+    unsigned char *ring = smem_raw + (size_t)warp * 2 * bufbytes;
+    const uint32_t ring_u32 = smem_u32(ring);
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCostConsumerWarps); }
+    if (lane == 0) {
+        mbar_init(&W.bar[0], 1); mbar_init(&W.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
-    const int per = (A.npairs + gridDim.x - 1) / gridDim.x;
-    const int begin = min(A.npairs, (int)blockIdx.x * per);
-    const int end = min(A.npairs, begin + per);
-
-    if (warp == 0) {
-        // ------------------------------ producer ------------------------------
-        int64_t tok1, tok2;
-        { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
-        int cur = begin;
-        int it = 0;
-        for (;; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            CostStage &G = stage[s];
-            mbar_wait(&empty_bar[s], ph ^ 1u);                      // stage drained (passes at once the first time round)
-            if (it >= S) {                                          // epilogue of the group that lived here
-                if (lane < G.nunits && G.units[lane].ni > 0) A.maxc[G.units[lane].q] = __uint_as_float(G.umax[lane]);
-            }
-            __syncwarp();
-            if (cur >= end) {
-                // no more work: publish the stop marker once per remaining stage so that every consumer sees it
-                if (lane == 0) { G.nunits = 0; G.nrows = 0; G.ntiles = -1; G.taskctr = 0; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[s]);
-                break;
-            }
-            const int q = cur + lane;
-            int u1 = 0, u2 = 0;
-            if (q < end) { const int u = A.u12[q]; u1 = u & 0xffff; u2 = u >> 16; }
-            if (u1 > A.tb || u2 > A.tb) { u1 = 0; u2 = 0; }         // handled by the large-pair kernel
-            const int tr = pick_orientation(u1, u2);
-            const int rows = u1 + u2;
-            const int tiles = (u1 > 0) ? unit_tiles(u1, u2, tr) : 0;
-            int rs = rows, ts = tiles;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int r = __shfl_up_sync(kFull, rs, o), t2 = __shfl_up_sync(kFull, ts, o);
-                if (lane >= o) { rs += r; ts += t2; }
-            }
-            const unsigned fits = __ballot_sync(kFull, rs <= A.rcap && q < end);
-            const int cnt = (fits == kFull) ? 32 : (__ffs(~fits) - 1);   // >= 1: one pair always fits
-            if (lane < cnt) {
-                CostUnit un;
-                un.q = q; un.rowbase = rs - rows; un.i0 = 0; un.ni = u1; un.j0 = 0; un.nj = u2; un.u2 = u2;
-                un.tilebase = ts - tiles; un.tr = tr; un._pad = 0;
-                int64_t aa; int l;
-                doc_span(A.s1, A.p0 + q, aa, l); un.o1 = aa - tok1;
-                doc_span(A.s2, A.p0 + q, aa, l); un.o2 = aa - tok2;
-                G.units[lane] = un;
-                G.umax[lane] = 0u;
-            }
-            const int total_rows = __shfl_sync(kFull, rs, cnt - 1);
-            const int total_tiles = __shfl_sync(kFull, ts, cnt - 1);
-            if (lane == 0) { G.nunits = cnt; G.nrows = total_rows; G.ntiles = total_tiles; G.taskctr = 0; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)total_rows * (uint32_t)A.rowbytes);
-            __syncwarp();
-            float *rowsbuf = rows_all + (size_t)s * stage_floats;
-            for (int rr = lane; rr < total_rows; rr += kWarp) {
-                int g = 0;
-                while (g + 1 < cnt && G.units[g + 1].rowbase <= rr) ++g;
-                const CostUnit &un = G.units[g];
-                const int local = rr - un.rowbase;
-                const int row = local < un.ni ? A.rows1[un.o1 + local] : A.rows2[un.o2 + (local - un.ni)];
-                tma_row_g2s(rowsbuf + (size_t)rr * A.ldr, A.vc.table + (int64_t)row * A.vc.ld, (uint32_t)A.rowbytes, &full_bar[s]);
-            }
-            cur += cnt;
-        }
-        // drain: the groups still in flight hand their maxima over when their stage empties
-        for (int k = 1; k < S; ++k) {
-            const int it2 = it + k;
-            const int s = it2 % S;
-            if (it2 < S) continue;                                  // that stage was never used
-            const uint32_t ph = (uint32_t)(it2 / S) & 1u;
-            CostStage &G = stage[s];
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            if (lane < G.nunits && G.units[lane].ni > 0) A.maxc[G.units[lane].q] = __uint_as_float(G.umax[lane]);
-            __syncwarp();
-        }
-    } else {
-        // ------------------------------ consumers ------------------------------
-        constexpr int TPW = 32 / (2 * PL);
-        for (int it = 0;; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            CostStage &G = stage[s];
-            mbar_wait(&full_bar[s], ph);
-            const int ntiles = G.ntiles;
-            if (ntiles < 0) break;                                  // stop marker
-            const int nunits = G.nunits;
-            const float *rowsbuf = rows_all + (size_t)s * stage_floats;
-            for (;;) {
-                int t0 = 0;
-                if (lane == 0) t0 = atomicAdd(&G.taskctr, TPW);
-                t0 = __shfl_sync(kFull, t0, 0);
-                if (t0 >= ntiles) break;
-                run_tile_batch<PL>(A, G.units, nunits, ntiles, t0, rowsbuf, G.umax);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
-        }
-    }
-}
-
-// Large pairs (a side with more than tb unique rows): one CTA per pair, tb x tb blocks in turn,
-// staged with plain coalesced 128-bit loads (rare path: documents longer than 32 unique tokens).
-template <int PL>
-__global__ void __launch_bounds__(kCostThreads)
-cost_tiles_large_kernel(const __grid_constant__ CostArgs A)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *rowsbuf = reinterpret_cast<float *>(smem_raw);
-    __shared__ CostUnit unit;
-    __shared__ unsigned umax;
-    constexpr int TPW = 32 / (2 * PL);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
-    const int d4 = A.vc.ld >> 2;
-    for (int q = blockIdx.x; q < A.npairs; q += gridDim.x) {
-        const int u = A.u12[q];
-        const int u1 = u & 0xffff, u2 = u >> 16;
-        if (u1 <= A.tb && u2 <= A.tb) continue;
-        if (threadIdx.x == 0) umax = 0u;
-        for (int bi = 0; bi < u1; bi += A.tb)
-            for (int bj = 0; bj < u2; bj += A.tb) {
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    CostUnit un;
-                    un.q = q; un.rowbase = 0; un.i0 = bi; un.ni = min(A.tb, u1 - bi);
-                    un.j0 = bj; un.nj = min(A.tb, u2 - bj); un.u2 = u2; un.tilebase = 0;
-                    un.tr = pick_orientation(un.ni, un.nj); un._pad = 0;
-                    int64_t aa; int l;
-                    doc_span(A.s1, A.p0 + q, aa, l); un.o1 = aa - tok1;
-                    doc_span(A.s2, A.p0 + q, aa, l); un.o2 = aa - tok2;
-                    unit = un;
-                }
-                __syncthreads();
-                const int nrows = unit.ni + unit.nj;
-                for (int rr = warp; rr < nrows; rr += nwarps) {
-                    const int row = rr < unit.ni ? A.rows1[unit.o1 + unit.i0 + rr] : A.rows2[unit.o2 + unit.j0 + (rr - unit.ni)];
-                    const float4 *src = reinterpret_cast<const float4 *>(A.vc.table + (int64_t)row * A.vc.ld);
-                    float4 *dst = reinterpret_cast<float4 *>(rowsbuf + (size_t)rr * A.ldr);
-                    for (int k = lane; k < d4; k += kWarp) dst[k] = __ldg(src + k);
-                }
-                __syncthreads();
-                const int ntiles = unit_tiles(unit.ni, unit.nj, unit.tr);
-                for (int t0 = warp * TPW; t0 < ntiles; t0 += nwarps * TPW)
-                    run_tile_batch<PL>(A, &unit, 1, ntiles, t0, rowsbuf, &umax);
+
+    // ---- pair / block iterator (warp-uniform) ----
+    int qa = 0, qb = 0;                       // claimed pairs [qa, qb)
+    bool have_pair = false;
+    int pq = 0, pu1 = 0, pu2 = 0, BI = 1, BJ = 1, nbi = 0, nbj = 0, bi = 0, bj = 0;
+    int64_t po1 = 0, po2 = 0;
+
+    auto next_pair = [&]() -> bool {
+        for (;;) {
+            if (qa >= qb) {
+                int q0 = 0;
+                if (lane == 0) q0 = (int)atomicAdd(A.counter, (unsigned)kClaim);
+                q0 = __shfl_sync(kFull, q0, 0);
+                if (q0 >= A.npairs) return false;
+                qa = q0; qb = min(A.npairs, q0 + kClaim);
             }
-        __syncthreads();
-        if (threadIdx.x == 0) A.maxc[q] = __uint_as_float(umax);
-        __syncthreads();
+            const int q = qa++;
+            const int u = __ldg(A.u12 + q);
+            const int u1 = u & 0xffff, u2 = u >> 16;
+            if (u1 == 0 || u2 == 0) continue;             // early-out pairs have no tile
+            pq = q; pu1 = u1; pu2 = u2;
+            int64_t aa; int l;
+            doc_span(A.s1, A.p0 + q, aa, l); po1 = aa - tok1;
+            doc_span(A.s2, A.p0 + q, aa, l); po2 = aa - tok2;
+            choose_blocks(u1, u2, BI, BJ, nbi, nbj);
+            bi = 0; bj = 0;
+            return true;
+        }
+    };
+
+    // per-lane source row of the unit being issued, and unit geometry (warp-uniform)
+    const float *srcrow = nullptr;
+    int nsubsU[2] = { 0, 0 }, nrowsU[2] = { 0, 0 }, ntilesU[2] = { 0, 0 };
+
+    auto build_unit = [&](int slot) -> bool {
+        int nsubs = 0, rows = 0, tiles = 0;
+        int myrow = -1;
+        while (nsubs < kUnitSubs) {
+            if (!have_pair) { have_pair = next_pair(); if (!have_pair) break; }
+            const int i0 = bi * BI, j0 = bj * BJ;
+            const int ni = min(BI, pu1 - i0), nj = min(BJ, pu2 - j0);
+            const int tr = pick_orientation(ni, nj);
+            const int nt = unit_tiles(ni, nj, tr);
+            if (nsubs > 0 && (rows + ni + nj > kUnitRows || tiles + nt > kUnitTiles)) break;
+            if (lane == 0) {
+                CostSub sb;
+                sb.q = pq; sb.i0 = i0; sb.ni = ni; sb.j0 = j0; sb.nj = nj; sb.u2 = pu2; sb.tr = tr;
+                sb.tilebase = tiles; sb.rowbase = rows; sb._pad = 0; sb.o1 = po1; sb.o2 = po2;
+                W.subs[slot][nsubs] = sb;
+            }
+            const int local = lane - rows;
+            if (local >= 0 && local < ni + nj)
+                myrow = local < ni ? __ldg(A.rows1 + po1 + i0 + local) : __ldg(A.rows2 + po2 + j0 + (local - ni));
+            rows += ni + nj; tiles += nt; ++nsubs;
+            if (++bj == nbj) { bj = 0; if (++bi == nbi) have_pair = false; }
+        }
+        nsubsU[slot] = nsubs; nrowsU[slot] = rows; ntilesU[slot] = tiles;
+        if (nsubs == 0) return false;
+        srcrow = A.vc.table + (int64_t)(myrow < 0 ? 0 : myrow) * A.vc.ld;
+        __syncwarp();
+        return true;
+    };
+
+    unsigned seq = 0;                         // chunks issued so far (buffer = seq & 1)
+    auto issue = [&](int slot, int c) {
+        const CostChunk ck = A.chunks[c];
+        const int b = seq & 1;
+        fence_proxy_async();                  // generic-proxy reads of this buffer precede the async-proxy writes
+        if (lane == 0) mbar_arrive_expect_tx(&W.bar[b], (uint32_t)nrowsU[slot] * ck.bytes);
+        __syncwarp();
+        if (lane < nrowsU[slot])
+            tma_row_g2s(ring_u32 + b * bufbytes + lane * A.pitch, srcrow + ck.foff, ck.bytes, &W.bar[b]);
+        ++seq;
+    };
+
+    int cur = 0;
+    if (!build_unit(cur)) return;
+    issue(cur, 0);
+    unsigned done = 0;                        // chunks consumed so far
+    const int pitchf = A.pitch >> 2;
+
+    for (;;) {
+        // ---- this lane pair's tile task in the current unit ----
+        const int ntiles = ntilesU[cur];
+        const bool live = lp < ntiles;
+        const int t = live ? lp : 0;
+        int g = 0;
+        while (g + 1 < nsubsU[cur] && W.subs[cur][g + 1].tilebase <= t) ++g;
+        const CostSub sb = W.subs[cur][g];
+        const int local = t - sb.tilebase;
+        const int na = sb.tr ? sb.nj : sb.ni, nb = sb.tr ? sb.ni : sb.nj;
+        const int abase = sb.rowbase + (sb.tr ? sb.ni : 0), bbase = sb.rowbase + (sb.tr ? 0 : sb.ni);
+        const int TI = (na + 1) >> 1, TJ = (nb + 3) >> 2;
+        const int ti = local / TJ, tj = local - ti * TJ;
+        int ia[2], jb[4], ra[2], rb[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { ia[r] = ti + r * TI; ra[r] = (abase + (ia[r] < na ? ia[r] : ti)) * pitchf; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { jb[c] = tj + c * TJ; rb[c] = (bbase + (jb[c] < nb ? jb[c] : tj)) * pitchf; }
+
+        Q4 acc[8];
+        float st[kStackDepth][4];
+        bool have_next = false;
+        int nxt = cur ^ 1;
+        for (int c = 0; c < A.nchunks; ++c) {
+            // keep one chunk in flight behind the one being summed
+            if (c + 1 < A.nchunks) issue(cur, c + 1);
+            else { have_next = build_unit(nxt); if (have_next) issue(nxt, 0); }
+            const int b = done & 1;
+            mbar_wait(&W.bar[b], (done >> 1) & 1u);
+            const float *buf = reinterpret_cast<const float *>(ring + (size_t)b * bufbytes);
+            const float *a[2] = { buf + ra[0], buf + ra[1] };
+            const float *bb[4] = { buf + rb[0], buf + rb[1], buf + rb[2], buf + rb[3] };
+            const CostChunk ck = A.chunks[c];
+            float res[4];
+            if (chunk_2x4(ck, a, bb, half, A.negzero2, acc, res)) {
+                // push the leaf sum, then pop-add `adds` times (static indexing: the stack top is st[0])
+#pragma unroll
+                for (int k = kStackDepth - 1; k > 0; --k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st[k][j] = st[k - 1][j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st[0][j] = res[j];
+                for (int k = 0; k < ck.adds; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st[0][j] = __fadd_rn(st[1][j], st[0][j]);
+#pragma unroll
+                    for (int m = 1; m < kStackDepth - 1; ++m)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) st[m][j] = st[m + 1][j];
+                }
+            }
+            ++done;
+            __syncwarp();                     // every lane is done reading buffer b before it is refilled
+        }
+        // ---- epilogue: distances, tile store, per-pair maximum ----
+        float mx = 0.f;
+        if (live) {
+            float *tile_p = A.tiles + (int64_t)sb.q * A.tile_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cidx = 2 * j + half;
+                const int r = cidx >> 2, cc = cidx & 3;
+                const int iar = r ? ia[1] : ia[0];
+                const int jbc = cc == 0 ? jb[0] : (cc == 1 ? jb[1] : (cc == 2 ? jb[2] : jb[3]));
+                if (iar < na && jbc < nb) {
+                    const float v = __fsqrt_rn(st[0][j]);
+                    const int i = sb.i0 + (sb.tr ? jbc : iar);
+                    const int jj = sb.j0 + (sb.tr ? iar : jbc);
+                    tile_p[(int64_t)i * sb.u2 + jj] = v;
+                    mx = fmaxf(mx, v);
+                }
+            }
+        }
+        const unsigned mxb = __float_as_uint(mx);            // distances are >= 0: uint order == float order
+        for (int s = 0; s < nsubsU[cur]; ++s) {
+            const unsigned m = __reduce_max_sync(kFull, (live && g == s) ? mxb : 0u);
+            if (lane == 0 && m) atomicMax(A.maxc + W.subs[cur][s].q, m);
+        }
+        if (!have_next) break;
+        cur = nxt;
     }
 }
 
 // init_sims(replace=True): v /= sqrt((v ** 2).sum(-1)) per row, float32, numpy summation order.
 // One-off at table load (src/wmd.py:54); one thread per row.
+constexpr int kPlanDepth = 8;
 __global__ void normalize_rows_kernel(float *table, int64_t V, int32_t d, int32_t ld, SumPlan plan)
 {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -92,6 +93,8 @@ struct wmd_engine {
     int64_t nmap = 0;
     int32_t *rank = nullptr;
     SumPlan plan;
+    CostChunk cost_chunks[kMaxChunks];           // K2's chunk program (the plan's leaves cut into staged pieces)
+    int32_t cost_nchunks = 0, cost_pitch = 0, cost_ctas_per_sm = 1;
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr }, ev_slot[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
@@ -117,6 +120,62 @@ void build_plan_rec(int start, int n, SumPlan &pl, bool &ok)
     build_plan_rec(start, n2, pl, ok);
     build_plan_rec(start + n2, n - n2, pl, ok);
     if (ok) pl.adds[pl.nops - 1]++;
+}
+
+// Cuts the plan's leaves into K2's staged chunks (<= max_iters 8-float iterations per chunk; the
+// len % 8 tail rides on a leaf's last chunk) and sizes the per-warp ring.
+int build_cost_chunks(wmd_engine *E, int max_iters)
+{
+    const SumPlan &pl = E->plan;
+    int n = 0, depth = 0, maxdepth = 0, maxbytes = 16;
+    for (int o = 0; o < pl.nops; ++o) {
+        const int start = pl.start[o], len = pl.len[o];
+        if (start % 8) return fail(WMD_EINVAL, "internal: leaf start %d is not a multiple of 8", start);
+        if (len < 8) {
+            if (n >= kMaxChunks) return fail(WMD_EINVAL, "embedding width %d needs too many chunks", E->d);
+            CostChunk c{};
+            c.foff = (uint16_t)start; c.bytes = (uint16_t)(((len * 4) + 15) & ~15); c.niter = 0; c.tail = (uint8_t)len;
+            c.flags = 1 | 2 | 4; c.adds = (uint8_t)pl.adds[o];
+            E->cost_chunks[n++] = c;
+            maxbytes = std::max(maxbytes, (int)c.bytes);
+        } else {
+            const int iters = len / 8, tail = len % 8;
+            const int pieces = (iters + max_iters - 1) / max_iters;
+            int done = 0;
+            for (int k = 0; k < pieces; ++k) {
+                if (n >= kMaxChunks) return fail(WMD_EINVAL, "embedding width %d needs too many chunks", E->d);
+                const int it = (iters - done + (pieces - k) - 1) / (pieces - k);      // balanced pieces
+                const bool last = k == pieces - 1;
+                CostChunk c{};
+                c.foff = (uint16_t)(start + 8 * done);
+                const int floats = 8 * it + (last ? tail : 0);
+                c.bytes = (uint16_t)(((floats * 4) + 15) & ~15);
+                c.niter = (uint16_t)it; c.tail = (uint8_t)(last ? tail : 0);
+                c.flags = (uint8_t)((k == 0 ? 1 : 0) | (last ? 2 : 0));
+                c.adds = (uint8_t)(last ? pl.adds[o] : 0);
+                E->cost_chunks[n++] = c;
+                maxbytes = std::max(maxbytes, (int)c.bytes);
+                done += it;
+            }
+        }
+        depth += 1; maxdepth = std::max(maxdepth, depth); depth -= pl.adds[o];
+    }
+    if (maxdepth > kStackDepth) return fail(WMD_EINVAL, "embedding width %d too large (summation tree deeper than %d)", E->d, kStackDepth);
+    E->cost_nchunks = n;
+    int pitch = (maxbytes + 63) & ~63;                       // == 32 (mod 64): LDS.128 of 4 adjacent rows hit 4 bank groups
+    pitch += 32;
+    E->cost_pitch = pitch;
+    const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * pitch;
+    if (smem > E->smem_optin) return fail(WMD_EINVAL, "embedding width %d does not fit the shared-memory ring", E->d);
+    cudaError_t e = cudaFuncSetAttribute(cost_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(WMD_ECUDA, "cudaFuncSetAttribute(cost_tiles_kernel): %s", cudaGetErrorString(e));
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cost_tiles_kernel, kCostThreads, smem);
+    if (e != cudaSuccess || nb < 1) return fail(WMD_ECUDA, "cost_tiles_kernel cannot be resident (%s)", cudaGetErrorString(e));
+    int cap = 4;                                             // 16 warps / SM: leaves room for the co-resident solver
+    if (const char *v = getenv("WMD_COST_CTAS_PER_SM")) cap = std::max(1, atoi(v));
+    E->cost_ctas_per_sm = std::min(nb, cap);
+    return WMD_OK;
 }
 
 struct Prof {
@@ -184,64 +243,21 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
     // ---- K2
     {
         CostArgs A;
-        A.vc = vc; A.plan = E->plan; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
-        int ldr4 = E->ld / 4;
-        if ((ldr4 & 1) == 0) ldr4++;
-        A.ldr = ldr4 * 4;
-        A.rowbytes = E->ld * 4;
+        A.vc = vc; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
+        A.nchunks = E->cost_nchunks; A.pitch = E->cost_pitch; A._pad = 0;
+        memcpy(A.chunks, E->cost_chunks, sizeof A.chunks);
         A.negzero2 = 0x8000000080000000ull;
-        A._pad = 0;
-        const size_t srow = (size_t)A.ldr * 4;                       // bytes per staged row
-        const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 12 * 1024;   // static stage records + barriers
-        int tb = std::min(32, ML);
-        while (tb > 1 && (size_t)2 * (2 * tb) * srow > budget) tb >>= 1;
-        if ((size_t)2 * (2 * tb) * srow > budget) return fail(WMD_EINVAL, "embedding width %d does not fit the shared-memory ring", E->d);
-        int rcap = std::max(2 * tb, (int)((48 * 1024) / srow));
-        rcap = std::min(rcap, 1024);
-        int stages = (int)std::min<size_t>(kMaxStages, budget / ((size_t)rcap * srow));
-        if (stages < 2) { rcap = 2 * tb; stages = (int)std::min<size_t>(kMaxStages, budget / ((size_t)rcap * srow)); }
-        A.tb = tb; A.rcap = rcap; A.stages = stages;
-        const SumPlan &pl = E->plan;
-        int PL = 1;
-        bool minlen = true;
-        for (int o = 0; o < pl.nops; ++o) minlen = minlen && pl.len[o] >= 8;
-        if (minlen && pl.nops == 4 && pl.adds[0] == 0 && pl.adds[1] == 1 && pl.adds[2] == 0 && pl.adds[3] == 2) PL = 4;
-        else if (minlen && pl.nops == 2 && pl.adds[0] == 0 && pl.adds[1] == 1) PL = 2;
-        A.pl = PL;
         A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
-        A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride; A.maxc = W.maxc.as<float>();
-        const size_t smem = (size_t)stages * rcap * srow;
-        {
-            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
-            Prof pr(E, WMD_K_COST, st);
-            if (PL == 4) {
-                CK(cudaFuncSetAttribute(cost_tiles_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cost_tiles_kernel<4><<<grid, kCostThreads, smem, st>>>(A);
-            } else if (PL == 2) {
-                CK(cudaFuncSetAttribute(cost_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cost_tiles_kernel<2><<<grid, kCostThreads, smem, st>>>(A);
-            } else {
-                CK(cudaFuncSetAttribute(cost_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cost_tiles_kernel<1><<<grid, kCostThreads, smem, st>>>(A);
-            }
-            CK(cudaGetLastError());
-        }
-        if (ML > tb) {
-            const size_t smem_l = (size_t)2 * tb * srow;
-            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count * 2);
-            Prof pr(E, WMD_K_COST, st);
-            if (PL == 4) {
-                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-                cost_tiles_large_kernel<4><<<grid, kCostThreads, smem_l, st>>>(A);
-            } else if (PL == 2) {
-                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-                cost_tiles_large_kernel<2><<<grid, kCostThreads, smem_l, st>>>(A);
-            } else {
-                CK(cudaFuncSetAttribute(cost_tiles_large_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-                cost_tiles_large_kernel<1><<<grid, kCostThreads, smem_l, st>>>(A);
-            }
-            CK(cudaGetLastError());
-        }
+        A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride;
+        A.maxc = W.maxc.as<unsigned int>();
+        A.counter = W.counters.as<unsigned int>() + 8;
+        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(W.maxc.p, 0, (size_t)Bc * 4, st));
+        const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
+        const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
+        Prof pr(E, WMD_K_COST, st);
+        cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
+        CK(cudaGetLastError());
     }
     // ---- K5 (optional)
     if (O.rwmd) {
@@ -258,8 +274,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         CK(cudaGetLastError());
     }
     if (!O.solve) return WMD_OK;
-    // ---- K3
-    CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
+    // ---- K3 (work counters were zeroed before K2)
     for (int cls = kClsA; cls <= kClsC; ++cls) {
         if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
         if (cls == kClsC && ML < 64) continue;
@@ -478,6 +493,11 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
     bool ok = true;
     build_plan_rec(0, d, E->plan, ok);
     if (!ok) return bail(fail(WMD_EINVAL, "embedding width %d too large", d));
+    {
+        int max_iters = 5;
+        if (const char *v = getenv("WMD_COST_CHUNK_ITERS")) max_iters = std::max(1, std::min(16, atoi(v)));
+        if ((rc = build_cost_chunks(E, max_iters))) return bail(rc);
+    }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
     if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));
     if (cudaMemcpy2D(E->table, (size_t)E->ld * 4, table_host, (size_t)row_stride * 4, (size_t)d * 4, (size_t)V, cudaMemcpyHostToDevice) != cudaSuccess)
