@@ -56,6 +56,7 @@ struct CostArgs {
     int32_t npairs;                  // pairs in this launch
     int32_t nchunks;
     int32_t pitch;                   // bytes between staged rows (== 32 mod 64: conflict-free LDS.128)
+    int32_t fast_R, fast_T;          // pairs that fit a planned stage (cost_fast.cuh) are skipped; 0 = take everything
     int32_t _pad;
     unsigned long long negzero2;     // 0x8000000080000000: (-0.0f, -0.0f), opaque to ptxas
     const int32_t *rows1, *rows2;    // from K1
@@ -145,6 +146,12 @@ __device__ __forceinline__ int pick_orientation(int ni, int nj)
     const int p0 = ((ni + 1) >> 1) * ((nj + 3) >> 2);              // tile tasks, 2-side along doc1
     const int p1 = ((nj + 1) >> 1) * ((ni + 3) >> 2);
     return p1 < p0 ? 1 : 0;
+}
+
+// A pair goes to the planned fast path (cost_fast.cuh) when its rows and tile tasks fit one stage.
+__device__ __forceinline__ bool fast_fits(int u1, int u2, int R, int T)
+{
+    return u1 > 0 && u2 > 0 && u1 + u2 <= R && unit_tiles(u1, u2, pick_orientation(u1, u2)) <= T;
 }
 
 // One chunk of a leaf for the 2x4 cells (a_r, b_c), c = 4r + cc.  `half` selects accumulators
@@ -279,6 +286,7 @@ cost_tiles_kernel(const __grid_constant__ CostArgs A)
             const int u = __ldg(A.u12 + q);
             const int u1 = u & 0xffff, u2 = u >> 16;
             if (u1 == 0 || u2 == 0) continue;             // early-out pairs have no tile
+            if (A.fast_R > 0 && fast_fits(u1, u2, A.fast_R, A.fast_T)) continue;
             pq = q; pu1 = u1; pu2 = u2;
             int64_t aa; int l;
             doc_span(A.s1, A.p0 + q, aa, l); po1 = aa - tok1;

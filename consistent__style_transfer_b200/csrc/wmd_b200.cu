@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "nbow.cuh"
 #include "cost.cuh"
+#include "cost_fast.cuh"
 #include "solve.cuh"
 #include "rwmd.cuh"
 
@@ -67,13 +68,13 @@ struct Workspace {
     DevBuf ids1, ids2, off1, off2;              // staged inputs (host entries)
     DevBuf rows1, cnt1, ip1, rows2, cnt2, ip2;  // per token slot
     DevBuf u12, meta, pqn, extra, maxc;         // per pair
-    DevBuf tiles, out, status, scratch;
+    DevBuf tiles, out, status, scratch, plan;
     DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
     DevBuf counters;                            // 4 x unsigned
     void release()
     {
         DevBuf *all[] = { &ids1, &ids2, &off1, &off2, &rows1, &cnt1, &ip1, &rows2, &cnt2, &ip2, &u12, &meta, &pqn,
-                          &extra, &maxc, &tiles, &out, &status, &scratch, &lb, &l1, &l2, &am1, &am2, &counters };
+                          &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &lb, &l1, &l2, &am1, &am2, &counters };
         for (DevBuf *b : all) b->release();
     }
 };
@@ -95,6 +96,8 @@ struct wmd_engine {
     SumPlan plan;
     CostChunk cost_chunks[kMaxChunks];           // K2's chunk program (the plan's leaves cut into staged pieces)
     int32_t cost_nchunks = 0, cost_pitch = 0, cost_ctas_per_sm = 1;
+    int32_t fast_R = 0, fast_S = 0, fast_ldr = 0, fast_PL = 1;   // planned fast path (cost_fast.cuh); fast_R == 0: disabled
+    size_t fast_smem = 0;
     cudaStream_t streams[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr }, ev_slot[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
@@ -178,6 +181,37 @@ int build_cost_chunks(wmd_engine *E, int max_iters)
     return WMD_OK;
 }
 
+// Sizes the planned fast path's stage ring for this embedding width (cost_fast.cuh).
+int setup_fast_path(wmd_engine *E)
+{
+    E->fast_R = 0;
+    if (const char *v = getenv("WMD_COST_FAST")) { if (atoi(v) == 0) return WMD_OK; }
+    int ldr4 = E->ld / 4;
+    if ((ldr4 & 1) == 0) ldr4++;
+    const int ldr = ldr4 * 4;
+    const size_t pitch = (size_t)ldr * 4;
+    int R = (int)std::min<size_t>(kStageRowsMax, (48 * 1024) / pitch);
+    if (R < 8) return WMD_OK;                                 // very wide embeddings: general kernel only
+    const size_t stage_bytes = (size_t)kStageDescBytes + (size_t)R * pitch;
+    const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 1024;    // static barriers / counters
+    int S = (int)std::min<size_t>(kFastMaxStages, budget / stage_bytes);
+    if (S < 2) return WMD_OK;
+    const SumPlan &pl = E->plan;
+    int PL = 1;
+    bool minlen = true;
+    for (int o = 0; o < pl.nops; ++o) minlen = minlen && pl.len[o] >= 8;
+    if (minlen && pl.nops == 4 && pl.adds[0] == 0 && pl.adds[1] == 1 && pl.adds[2] == 0 && pl.adds[3] == 2) PL = 4;
+    else if (minlen && pl.nops == 2 && pl.adds[0] == 0 && pl.adds[1] == 1) PL = 2;
+    const size_t smem = (size_t)S * stage_bytes;
+    cudaError_t e;
+    if (PL == 4) e = cudaFuncSetAttribute(cost_tiles_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (PL == 2) e = cudaFuncSetAttribute(cost_tiles_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else e = cudaFuncSetAttribute(cost_tiles_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(WMD_ECUDA, "cudaFuncSetAttribute(cost_tiles_fast_kernel): %s", cudaGetErrorString(e));
+    E->fast_R = R; E->fast_S = S; E->fast_ldr = ldr; E->fast_PL = PL; E->fast_smem = smem;
+    return WMD_OK;
+}
+
 struct Prof {
     wmd_engine *E; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     Prof(wmd_engine *E_, int kind_, cudaStream_t st_) : E(E_), kind(kind_), st(st_)
@@ -240,24 +274,56 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         nbow_pairs_kernel<<<grid, wpb * 32, smem, st>>>(s1, s2, vc, p0, Bc, Lp, pw, O.out, O.status);
         CK(cudaGetLastError());
     }
-    // ---- K2
+    // ---- K2: planned fast path for pairs that fit a stage, general kernel for the rest
     {
-        CostArgs A;
-        A.vc = vc; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
-        A.nchunks = E->cost_nchunks; A.pitch = E->cost_pitch; A._pad = 0;
-        memcpy(A.chunks, E->cost_chunks, sizeof A.chunks);
-        A.negzero2 = 0x8000000080000000ull;
-        A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
-        A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride;
-        A.maxc = W.maxc.as<unsigned int>();
-        A.counter = W.counters.as<unsigned int>() + 8;
         CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
         CK(cudaMemsetAsync(W.maxc.p, 0, (size_t)Bc * 4, st));
-        const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
-        const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
-        Prof pr(E, WMD_K_COST, st);
-        cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
-        CK(cudaGetLastError());
+        const int R = E->fast_R, T = kStageTilesMax;
+        bool need_general = true;
+        if (R > 0) {
+            if ((rc = W.plan.ensure((size_t)Bc * sizeof(StageRec)))) return rc;
+            PlanArgs P;
+            P.s1 = s1; P.s2 = s2; P.p0 = p0; P.npairs = Bc; P.R = R; P.T = T; P._pad = 0;
+            P.rows1 = pw.rows1; P.rows2 = pw.rows2; P.u12 = pw.u12;
+            P.stages = W.plan.as<StageRec>(); P.nstages = W.counters.as<unsigned int>() + 9;
+            const int pblocks = (int)std::min<int64_t>(((int64_t)Bc + 127) / 128, (int64_t)E->sm_count * 16);
+            {
+                Prof pr(E, WMD_K_COST, st);
+                cost_plan_kernel<<<pblocks, 128, 0, st>>>(P);
+                CK(cudaGetLastError());
+            }
+            FastArgs F;
+            F.vc = vc; F.plan = E->plan; F.R = R; F.S = E->fast_S; F.ldr = E->fast_ldr; F.rowbytes = E->ld * 4;
+            F.negzero2 = 0x8000000080000000ull;
+            F.stages = P.stages; F.nstages = P.nstages;
+            F.tiles = W.tiles.as<float>(); F.tile_stride = tile_stride; F.maxc = W.maxc.as<unsigned int>();
+            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
+            Prof pr(E, WMD_K_COST, st);
+            if (E->fast_PL == 4) cost_tiles_fast_kernel<4><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            else if (E->fast_PL == 2) cost_tiles_fast_kernel<2><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            else cost_tiles_fast_kernel<1><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            CK(cudaGetLastError());
+            // every pair of this chunk fits a stage when the longest possible one does
+            const int a = std::min(ml1, ml2), b = std::max(ml1, ml2);
+            const int worst_tiles = std::min(((a + 1) / 2) * ((b + 3) / 4), ((b + 1) / 2) * ((a + 3) / 4));
+            need_general = ml1 + ml2 > R || worst_tiles > T;
+        }
+        if (need_general) {
+            CostArgs A;
+            A.vc = vc; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
+            A.nchunks = E->cost_nchunks; A.pitch = E->cost_pitch; A.fast_R = R; A.fast_T = T; A._pad = 0;
+            memcpy(A.chunks, E->cost_chunks, sizeof A.chunks);
+            A.negzero2 = 0x8000000080000000ull;
+            A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
+            A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride;
+            A.maxc = W.maxc.as<unsigned int>();
+            A.counter = W.counters.as<unsigned int>() + 8;
+            const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
+            const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
+            Prof pr(E, WMD_K_COST, st);
+            cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
+            CK(cudaGetLastError());
+        }
     }
     // ---- K5 (optional)
     if (O.rwmd) {
@@ -494,9 +560,10 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
     build_plan_rec(0, d, E->plan, ok);
     if (!ok) return bail(fail(WMD_EINVAL, "embedding width %d too large", d));
     {
-        int max_iters = 5;
+        int max_iters = 10;
         if (const char *v = getenv("WMD_COST_CHUNK_ITERS")) max_iters = std::max(1, std::min(16, atoi(v)));
         if ((rc = build_cost_chunks(E, max_iters))) return bail(rc);
+        if ((rc = setup_fast_path(E))) return bail(rc);
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
     if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));
