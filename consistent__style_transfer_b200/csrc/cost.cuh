@@ -97,13 +97,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
+    for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > (1ll << 33)) __trap();       // ~4 s: a protocol bug must fault, never hang the GPU
+        if (spins > (1u << 28)) __trap();                 // seconds: a protocol bug must fault, never hang the GPU
     }
 }
 __device__ __forceinline__ void tma_row_g2s(uint32_t dst, const void *src, uint32_t bytes, unsigned long long *bar)

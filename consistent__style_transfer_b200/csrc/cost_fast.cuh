@@ -82,9 +82,11 @@ cost_plan_kernel(const __grid_constant__ PlanArgs A)
             const int r = __shfl_up_sync(kFull, rs, o), t2 = __shfl_up_sync(kFull, ts, o);
             if (lane >= o) { rs += r; ts += t2; }
         }
-        // greedy packing of consecutive pairs into stages
+        // greedy packing of consecutive pairs into stages (stage numbers are reserved once per warp:
+        // one same-address atomic per stage serialises in L2 and cost 40 us per launch)
         int my_stage = -1, my_rowbase = 0, my_tilebase = 0;
-        int start = 0, base_r = 0, base_t = 0;
+        int hdr_r = 0, hdr_t = 0;                                     // set on the first lane of every stage
+        int start = 0, base_r = 0, base_t = 0, nlocal = 0;
         while (start < 32) {
             const bool fit = lane >= start && rs - base_r <= A.R && ts - base_t <= A.T;
             const unsigned fm = __ballot_sync(kFull, fit) >> start;
@@ -94,17 +96,17 @@ cost_plan_kernel(const __grid_constant__ PlanArgs A)
             const int tot_r = __shfl_sync(kFull, rs, end - 1) - base_r;
             const int tot_t = __shfl_sync(kFull, ts, end - 1) - base_t;
             if (tot_r > 0) {
-                int sidx = 0;
-                if (lane == 0) {
-                    sidx = (int)atomicAdd(A.nstages, 1u);
-                    A.stages[sidx].nrows = tot_r;
-                    A.stages[sidx].ntiles = tot_t;
-                }
-                sidx = __shfl_sync(kFull, sidx, 0);
-                if (lane >= start && lane < end) { my_stage = sidx; my_rowbase = rs - rows - base_r; my_tilebase = ts - tiles - base_t; }
+                if (lane >= start && lane < end) { my_stage = nlocal; my_rowbase = rs - rows - base_r; my_tilebase = ts - tiles - base_t; }
+                if (lane == start) { hdr_r = tot_r; hdr_t = tot_t; }
+                ++nlocal;
             }
             base_r += tot_r; base_t += tot_t; start = end;
         }
+        int sbase = 0;
+        if (lane == 0 && nlocal) sbase = (int)atomicAdd(A.nstages, (unsigned)nlocal);
+        sbase = __shfl_sync(kFull, sbase, 0);
+        if (my_stage >= 0) my_stage += sbase;
+        if (hdr_r > 0) { A.stages[my_stage].nrows = hdr_r; A.stages[my_stage].ntiles = hdr_t; }
         // every pair writes its own rows and tile descriptors
         if (my_stage >= 0 && rows > 0) {
             StageRec &S = A.stages[my_stage];
