@@ -1,0 +1,328 @@
+// allpairs.cuh -- all-pairs top-k WMD with RWMD pruning (BASELINE config 4; not in the reference).
+//
+// For every document i of set A, the k documents j of set B with the smallest WMD(i, j)
+// (ties: lower j), exact -- the values are the same pyemd-grid optima the pair path returns.
+// Prefetch-and-prune after Kusner et al. 2015, with the relaxed bound evaluated the linear-complexity
+// way of Atasu et al. 2017 (LC-RWMD) so that the 10^10 bounds of a 100k x 100k problem cost ~10 FMAs each:
+//   D[a][b]   float32 distance between every two table rows, computed by the K2 cost kernels
+//             themselves on blocks of consecutive rows (bit-identical to the pair path's cost tiles);
+//   Z_B[w][j] = min over the tokens t of B_j of D[w][t]        (one pass over B, V x |B| floats)
+//   L1(i, j)  = sum over tokens w of A_i of weight(w) * Z_B[w][j]      (cost of moving A_i's mass greedily)
+//   L2(i, j)  = sum over tokens t of B_j of weight(t) * Z_A[t][i]
+//   LB(i, j)  = max(L1, L2) <= WMD_real(i, j)
+// Round 1 solves exactly the k candidates with the smallest LB per row; their k-th distance thr_i
+// bounds the answer, so round 2 solves every remaining j with LB(i, j) <= thr_i + kLbMargin and
+// nothing else can enter the top k.  kLbMargin covers the gap between the real-valued optimum that
+// RWMD bounds and the 1e-6-grid optimum pyemd returns: costs round by <= 0.5e-6 * maxC per unit of
+// mass and the <= 512 masses by <= 0.5e-6 each, i.e. |WMD_pyemd - WMD_real| < 3e-4 * maxC / 2 ... we
+// use 1e-3, an absolute bound that is generous for unit vectors (maxC <= 2) and costs nothing.
+#pragma once
+#include "common.cuh"
+
+namespace wmd {
+
+constexpr double kLbMargin = 1e-3;
+
+// ---- D: scatter the cost tiles of row-block pairs into the V x V table --------------------------
+// pair q = (bi, bj), bi <= bj, blocks of BS consecutive table rows.
+__global__ void dtab_make_pairs_kernel(int32_t V, int32_t BS, int32_t nb, int64_t q0, int32_t npairs,
+                                       int32_t *rows1, int32_t *rows2, int32_t *u12, int32_t *bij)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npairs) return;
+    // unrank (bi, bj) from the global pair number over the upper triangle, row-major
+    int64_t g = q0 + q;
+    int bi = 0;
+    {
+        // row bi holds nb - bi pairs; solve by float estimate then fix up
+        const double nbd = (double)nb;
+        double est = nbd + 0.5 - sqrt((nbd + 0.5) * (nbd + 0.5) - 2.0 * (double)g);
+        bi = (int)est;
+        if (bi < 0) bi = 0;
+        if (bi >= nb) bi = nb - 1;
+        while (bi > 0 && (int64_t)bi * nb - (int64_t)bi * (bi - 1) / 2 > g) --bi;
+        while ((int64_t)(bi + 1) * nb - (int64_t)(bi + 1) * bi / 2 <= g) ++bi;
+    }
+    const int64_t before = (int64_t)bi * nb - (int64_t)bi * (bi - 1) / 2;
+    const int bj = bi + (int)(g - before);
+    const int n1 = min(BS, V - bi * BS), n2 = min(BS, V - bj * BS);
+    for (int k = 0; k < BS; ++k) {
+        rows1[(int64_t)q * BS + k] = k < n1 ? bi * BS + k : 0;
+        rows2[(int64_t)q * BS + k] = k < n2 ? bj * BS + k : 0;
+    }
+    u12[q] = n1 | (n2 << 16);
+    bij[2 * q] = bi; bij[2 * q + 1] = bj;
+}
+
+__global__ void dtab_scatter_kernel(int32_t V, int32_t BS, int32_t npairs, const int32_t *u12, const int32_t *bij,
+                                    const float *tiles, int64_t tile_stride, float *D)
+{
+    const int q = blockIdx.x;
+    if (q >= npairs) return;
+    const int u = u12[q], n1 = u & 0xffff, n2 = u >> 16;
+    const int bi = bij[2 * q], bj = bij[2 * q + 1];
+    const float *t = tiles + (int64_t)q * tile_stride;
+    for (int c = threadIdx.x; c < n1 * n2; c += blockDim.x) {
+        const int i = c / n2, j = c - i * n2;
+        const float v = t[c];
+        const int64_t a = (int64_t)bi * BS + i, b = (int64_t)bj * BS + j;
+        D[a * V + b] = v;
+        D[b * V + a] = v;
+    }
+}
+
+__global__ void table_max_kernel(const float *D, int64_t n, unsigned int *maxbits)
+{
+    unsigned m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(D[i]));                  // distances are >= 0: uint order == float order
+    m = __reduce_max_sync(kFull, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(maxbits, m);
+}
+
+// ---- Z[w][j] = min_t D[t][w] over the in-vocabulary rows t of document j --------------------------
+// rows / uniq: per-document unique rows at the CSR offsets (nbow_docs_kernel). Documents without
+// any in-vocabulary token get +inf (every WMD with them is +inf).
+struct ZArgs {
+    const float *D; int32_t V;
+    const int32_t *rows; const int64_t *off; const int32_t *uniq;
+    int64_t doc0; int32_t ndocs;              // documents [doc0, doc0 + ndocs) -> columns [0, ndocs)
+    float *Z; int64_t ldz;                    // Z[w * ldz + (j - doc0)]
+};
+
+__global__ void __launch_bounds__(1024)
+z_build_kernel(const __grid_constant__ ZArgs A)
+{
+    __shared__ float tile[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int w0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int j = j0 + y, w = w0 + x;
+    float best = __int_as_float(0x7f800000);
+    if (j < A.ndocs && w < A.V) {
+        const int64_t a = A.off[A.doc0 + j];
+        const int u = A.uniq[A.doc0 + j];
+        for (int k = 0; k < u; ++k) {
+            const int t = A.rows[a + k];
+            best = fminf(best, A.D[(int64_t)t * A.V + w]);
+        }
+    }
+    tile[y][x] = best;
+    __syncthreads();
+    const int jw = j0 + x, ww = w0 + y;
+    if (jw < A.ndocs && ww < A.V) A.Z[(int64_t)ww * A.ldz + jw] = tile[x][y];
+}
+
+// ---- LB tile: 32 query rows x 32 corpus columns per block -----------------------------------------
+struct LbArgs {
+    // query side (set A), rows [i0, i0 + ni)
+    const int32_t *rowsA, *cntA; const int64_t *offA; const int32_t *uniqA; const int32_t *nvalA;
+    int64_t i0; int32_t ni;
+    // corpus side (set B)
+    const int32_t *rowsB, *cntB; const int64_t *offB; const int32_t *uniqB; const int32_t *nvalB;
+    int32_t nB;
+    const float *ZB; int64_t ldzb;            // [V][nB]
+    const float *ZA; int64_t ldza;            // [V][ni] for this block of query rows
+    float *LB; int64_t ldlb;                  // [ni][nB]
+};
+
+__global__ void __launch_bounds__(1024)
+lb_tile_kernel(const __grid_constant__ LbArgs A)
+{
+    __shared__ double l2t[32][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int jb = blockIdx.x * 32, ib = blockIdx.y * 32;
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    // L2(i, j): lanes along i (Z_A rows are contiguous in i), y = j
+    {
+        const int j = jb + y, i = ib + x;
+        double acc = kInf;
+        if (j < A.nB && i < A.ni) {
+            const int n = A.nvalB[j];
+            if (n > 0) {
+                acc = 0.0;
+                const int64_t a = A.offB[j];
+                const int u = A.uniqB[j];
+                const double dn = (double)n;
+                for (int k = 0; k < u; ++k) {
+                    const double wgt = (double)A.cntB[a + k] / dn;
+                    acc += wgt * (double)A.ZA[(int64_t)A.rowsB[a + k] * A.ldza + i];
+                }
+            }
+        }
+        l2t[y][x] = acc;
+    }
+    __syncthreads();
+    // L1(i, j): lanes along j, y = i
+    {
+        const int i = ib + y, j = jb + x;
+        if (i < A.ni && j < A.nB) {
+            double acc = kInf;
+            const int n = A.nvalA[A.i0 + i];
+            if (n > 0) {
+                acc = 0.0;
+                const int64_t a = A.offA[A.i0 + i];
+                const int u = A.uniqA[A.i0 + i];
+                const double dn = (double)n;
+                for (int k = 0; k < u; ++k) {
+                    const double wgt = (double)A.cntA[a + k] / dn;
+                    acc += wgt * (double)A.ZB[(int64_t)A.rowsA[a + k] * A.ldzb + j];
+                }
+            }
+            const double l2 = l2t[x][y];
+            double lb = acc > l2 ? acc : l2;            // inf if either side is empty
+            // round DOWN to float so that the stored bound never exceeds the FP64 one
+            float f = __double2float_rd(lb);
+            A.LB[(int64_t)i * A.ldlb + j] = f;
+        }
+    }
+}
+
+// ---- per-row k-th smallest of LB (radix select on the float bits; all values are >= 0 or +inf) ----
+__global__ void __launch_bounds__(256)
+row_kth_kernel(const float *LB, int64_t ldlb, int32_t n, int32_t k, float *kth)
+{
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_k;
+    const unsigned *row = reinterpret_cast<const unsigned *>(LB + (int64_t)blockIdx.x * ldlb);
+    if (k > n) { if (threadIdx.x == 0) kth[blockIdx.x] = __int_as_float(0x7f800000); return; }
+    unsigned prefix = 0, mask = 0, kk = (unsigned)k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += 256) {
+            const unsigned v = row[j];
+            if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned acc = 0, b = 0;
+            for (; b < 256; ++b) { if (acc + hist[b] >= kk) break; acc += hist[b]; }
+            s_prefix = prefix | (b << shift);
+            s_k = kk - acc;
+        }
+        __syncthreads();
+        prefix = s_prefix; kk = s_k; mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kth[blockIdx.x] = __uint_as_float(prefix);
+}
+
+// ---- candidate lists: j with lo_i < LB(i, j) <= hi_i, ascending j ---------------------------------
+// pass 0 counts, pass 1 fills at the scanned offsets.  lo == nullptr: no lower limit.
+__global__ void __launch_bounds__(256)
+cand_rows_kernel(const float *LB, int64_t ldlb, int32_t n, const float *lo, const float *hi, int32_t fill,
+                 int32_t *counts, const int64_t *offsets, int32_t row0, int32_t *ci, int32_t *cj)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int r = blockIdx.x;
+    const float *row = LB + (int64_t)r * ldlb;
+    const float h = hi[r];
+    const bool has_lo = lo != nullptr;
+    const float l = has_lo ? lo[r] : 0.f;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    int total = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        bool take = false;
+        if (j < n) { const float v = row[j]; take = v <= h && (!has_lo || v > l); }
+        const unsigned bal = __ballot_sync(kFull, take);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; if (w < wid) before += c; all += c; }
+        if (fill && take) {
+            const int64_t pos = offsets[r] + total + before + __popc(bal & ((1u << lane) - 1));
+            ci[pos] = row0 + r; cj[pos] = j;
+        }
+        total += all;
+        __syncthreads();
+    }
+    if (!fill && threadIdx.x == 0) counts[r] = total;
+}
+
+// exclusive scan of up to a few thousand row counts (one block)
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t *counts, int32_t n, int64_t *offsets /* n + 1 */)
+{
+    __shared__ long long s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    long long sum = 0;
+    for (int i = b; i < e; ++i) sum += counts[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        for (int t = 0; t < 1024; ++t) { const long long v = s_part[t]; s_part[t] = acc; acc += v; }
+        offsets[n] = acc;
+    }
+    __syncthreads();
+    long long acc = s_part[threadIdx.x];
+    for (int i = b; i < e; ++i) { offsets[i] = acc; acc += counts[i]; }
+}
+
+// ---- per-row top-k merge ---------------------------------------------------------------------------
+// Row r merges its current best list (top_j / top_d, kcur[r] valid entries, sorted) with the new
+// candidates [offsets[r], offsets[r + 1]) and keeps the k smallest by (distance, j).  Distances are
+// >= 0 or +inf (NaN never occurs), so their bit patterns order like the values.
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(int32_t k, const int64_t *offsets, const int32_t *cj, const double *cd,
+                  int32_t *top_j, double *top_d, int32_t *kcur, float *thr /* k-th distance or +inf, rounded up */)
+{
+    extern __shared__ unsigned char sm_raw[];
+    unsigned long long *okey = reinterpret_cast<unsigned long long *>(sm_raw);      // [k] merged keys
+    int *oj = reinterpret_cast<int *>(okey + k);                                     // [k]
+    __shared__ unsigned long long s_bk[8];
+    __shared__ int s_bj[8];
+    __shared__ unsigned long long s_lastk;
+    __shared__ int s_lastj;
+    const int r = blockIdx.x;
+    const int64_t b = offsets[r], e = offsets[r + 1];
+    const int nold = kcur[r];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t total = (e - b) + nold;
+    const int nout = (int)(total < k ? total : k);
+    unsigned long long lastk = 0; int lastj = -1;                 // everything <= (lastk, lastj) is already taken
+    for (int o = 0; o < nout; ++o) {
+        unsigned long long bk = ~0ull; int bj = 0x7fffffff;
+        for (int64_t c = threadIdx.x; c < total; c += 256) {
+            unsigned long long key; int j;
+            if (c < nold) { key = (unsigned long long)__double_as_longlong(top_d[(int64_t)r * k + c]); j = top_j[(int64_t)r * k + c]; }
+            else { key = (unsigned long long)__double_as_longlong(cd[b + (c - nold)]); j = cj[b + (c - nold)]; }
+            const bool after = o == 0 || key > lastk || (key == lastk && j > lastj);
+            if (after && (key < bk || (key == bk && j < bj))) { bk = key; bj = j; }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(kFull, bk, s);
+            const int ojj = __shfl_xor_sync(kFull, bj, s);
+            if (ok < bk || (ok == bk && ojj < bj)) { bk = ok; bj = ojj; }
+        }
+        if (lane == 0) { s_bk[wid] = bk; s_bj[wid] = bj; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (s_bk[w] < bk || (s_bk[w] == bk && s_bj[w] < bj)) { bk = s_bk[w]; bj = s_bj[w]; }
+            okey[o] = bk; oj[o] = bj; s_lastk = bk; s_lastj = bj;
+        }
+        __syncthreads();
+        lastk = s_lastk; lastj = s_lastj;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nout; o += 256) {
+        top_d[(int64_t)r * k + o] = __longlong_as_double((long long)okey[o]);
+        top_j[(int64_t)r * k + o] = oj[o];
+    }
+    if (threadIdx.x == 0) {
+        kcur[r] = nout;
+        float t = __int_as_float(0x7f800000);
+        if (nout == k) t = __double2float_ru(__longlong_as_double((long long)okey[k - 1]) + kLbMargin);
+        thr[r] = t;
+    }
+}
+
+}  // namespace wmd

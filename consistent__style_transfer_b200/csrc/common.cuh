@@ -19,19 +19,28 @@ constexpr int kClsC = 3;                 // anything up to 256 x 257
 constexpr int kMetaSwap = 8;             // doc2 is the heavier (supplying) side
 
 // One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).
+// With sel != nullptr pair p uses document sel[p] (all-pairs candidate lists: many pairs share a
+// document), and the per-pair work slots are laid out at q * slot instead of at the CSR offsets.
 struct DocSide {
     const int32_t *ids;
     const int64_t *off;
     int32_t L;            // padded row length when off == nullptr
     int32_t pad_id;
     int32_t has_pad;
-    int32_t _r;
+    int32_t slot;         // work-slot pitch when sel != nullptr (>= the longest document)
+    const int32_t *sel;   // optional document index per pair
 };
 
 __device__ __forceinline__ void doc_span(const DocSide &s, int64_t p, int64_t &start, int &len)
 {
+    if (s.sel) p = s.sel[p];
     if (s.off) { start = s.off[p]; len = (int)(s.off[p + 1] - start); }
     else       { start = p * (int64_t)s.L; len = s.L; }
+}
+// offset of pair q's work slots (rows / counts / masses) inside the launch's per-token arrays
+__device__ __forceinline__ int64_t slot_off(const DocSide &s, int64_t tokbase, int q, int64_t start)
+{
+    return s.sel ? (int64_t)q * s.slot : start - tokbase;
 }
 
 struct Vocab {

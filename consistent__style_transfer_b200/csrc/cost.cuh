@@ -288,8 +288,8 @@ cost_tiles_kernel(const __grid_constant__ CostArgs A)
             if (A.fast_R > 0 && fast_fits(u1, u2, A.fast_R, A.fast_T)) continue;
             pq = q; pu1 = u1; pu2 = u2;
             int64_t aa; int l;
-            doc_span(A.s1, A.p0 + q, aa, l); po1 = aa - tok1;
-            doc_span(A.s2, A.p0 + q, aa, l); po2 = aa - tok2;
+            doc_span(A.s1, A.p0 + q, aa, l); po1 = slot_off(A.s1, tok1, q, aa);
+            doc_span(A.s2, A.p0 + q, aa, l); po2 = slot_off(A.s2, tok2, q, aa);
             choose_blocks(u1, u2, BI, BJ, nbi, nbj);
             bi = 0; bj = 0;
             return true;

@@ -112,7 +112,7 @@ cost_plan_kernel(const __grid_constant__ PlanArgs A)
             StageRec &S = A.stages[my_stage];
             int64_t a1, a2; int l;
             doc_span(A.s1, A.p0 + q, a1, l); doc_span(A.s2, A.p0 + q, a2, l);
-            const int32_t *r1 = A.rows1 + (a1 - tok1), *r2 = A.rows2 + (a2 - tok2);
+            const int32_t *r1 = A.rows1 + slot_off(A.s1, tok1, q, a1), *r2 = A.rows2 + slot_off(A.s2, tok2, q, a2);
             for (int k = 0; k < u1; ++k) S.rows[my_rowbase + k] = r1[k];
             for (int k = 0; k < u2; ++k) S.rows[my_rowbase + u1 + k] = r2[k];
             const int na = tr ? u2 : u1, nb = tr ? u1 : u2;

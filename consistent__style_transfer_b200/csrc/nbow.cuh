@@ -115,7 +115,7 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
         int n1, n2;
         const int u1 = side_unique(s1, a1, n1raw, vc, lane, skey, skeyF, srowt, scntT, srow1, scnt1, n1);
         const int u2 = side_unique(s2, a2, n2raw, vc, lane, skey, skeyF, srowt, scntT, srow2, scnt2, n2);
-        const int64_t o1 = a1 - tokbase1, o2 = a2 - tokbase2;
+        const int64_t o1 = slot_off(s1, tokbase1, q, a1), o2 = slot_off(s2, tokbase2, q, a2);
         st_tok += n1raw + n2raw;
 
         int meta = kClsNone;
@@ -202,7 +202,7 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
 // Stand-alone nBOW of documents (wmd_nbow_host): rows / counts / weights at the CSR offsets.
 __global__ void __launch_bounds__(256)
 nbow_docs_kernel(DocSide s, Vocab vc, int32_t ndocs, int32_t Lp,
-                 int32_t *rows, int32_t *counts, double *weights, int32_t *uniq)
+                 int32_t *rows, int32_t *counts, double *weights, int32_t *uniq, int32_t *nval)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -219,9 +219,9 @@ nbow_docs_kernel(DocSide s, Vocab vc, int32_t ndocs, int32_t Lp,
         const double dn = (double)n;
         for (int i = lane; i < u; i += kWarp) {
             rows[a + i] = srow[i]; counts[a + i] = scnt[i];
-            weights[a + i] = __ddiv_rn((double)scnt[i], dn);
+            if (weights) weights[a + i] = __ddiv_rn((double)scnt[i], dn);
         }
-        if (lane == 0) uniq[q] = u;
+        if (lane == 0) { uniq[q] = u; if (nval) nval[q] = n; }
         __syncwarp();
     }
 }

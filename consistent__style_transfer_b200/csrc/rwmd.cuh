@@ -36,7 +36,7 @@ rwmd_pairs_kernel(const __grid_constant__ RwmdArgs A)
         const int64_t p = A.p0 + q;
         int64_t a1, a2; int l;
         doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
-        const int64_t o1 = a1 - tok1, o2 = a2 - tok2;
+        const int64_t o1 = slot_off(A.s1, tok1, q, a1), o2 = slot_off(A.s2, tok2, q, a2);
         const int st = A.status[p];
         if (st == 1) {
             if (lane == 0) { A.lb[p] = __longlong_as_double(0x7ff0000000000000LL); if (A.l1) A.l1[p] = A.lb[p]; if (A.l2) A.l2[p] = A.lb[p]; }

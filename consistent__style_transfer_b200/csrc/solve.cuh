@@ -284,8 +284,8 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
             const bool swap = (meta & kMetaSwap) != 0;
             int64_t a1, a2; int l;
             doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
-            const int32_t *ipR = swap ? A.ip2 + (a2 - tok2) : A.ip1 + (a1 - tok1);   // supplying side
-            const int32_t *ipC = swap ? A.ip1 + (a1 - tok1) : A.ip2 + (a2 - tok2);
+            const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
+            const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
             const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
             int m = 0, n = 0, sumR = 0, sumC = 0;
             for (int base = 0; base < uR; base += kWarp) {       // compact the residual rows: (mass << 8) | index
@@ -386,8 +386,8 @@ emd_solve_kernel(const __grid_constant__ SolveArgs A)
             const bool swap = (meta & kMetaSwap) != 0;
             int64_t a1, a2; int l;
             doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
-            const int32_t *ipR = swap ? A.ip2 + (a2 - tok2) : A.ip1 + (a1 - tok1);   // supplying side
-            const int32_t *ipC = swap ? A.ip1 + (a1 - tok1) : A.ip2 + (a2 - tok2);
+            const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
+            const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
             const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
             // compact the residual rows / columns
             int m = 0, n = 0, sumR = 0, sumC = 0;

@@ -22,6 +22,7 @@
 #include "cost_fast.cuh"
 #include "solve.cuh"
 #include "rwmd.cuh"
+#include "allpairs.cuh"
 
 using namespace wmd;
 
@@ -102,6 +103,11 @@ struct wmd_engine {
     cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr }, ev_slot[2] = { nullptr, nullptr };
     bool slot_used[2] = { false, false };
     Workspace ws[2];
+    // all-pairs mode (allpairs.cuh): V x V distance table (lazy) and a grow-only workspace
+    float *dtab = nullptr;
+    float dmax = 0.f;
+    cudaStream_t ap_stream = nullptr;
+    DevBuf ap[32];
     unsigned long long *stats = nullptr;        // device [6]
     bool profiling = false;
     std::vector<ProfRec> prof;
@@ -240,6 +246,69 @@ struct ChunkOut {
     bool solve = true;
 };
 
+// K2: cost tiles of pairs [p0, p0 + Bc): the planned fast path for pairs that fit a stage, the
+// general kernel for the rest.  rows1 / rows2 / u12 come from K1 (or are synthesised by the
+// distance-table build); tiles is [Bc, tile_stride]; maxc receives the per-pair maximum (float bits).
+int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2, int64_t p0, int32_t Bc,
+                int32_t ml1, int32_t ml2, const int32_t *rows1, const int32_t *rows2, const int32_t *u12,
+                float *tiles, int64_t tile_stride, unsigned int *maxc)
+{
+    int rc;
+    const Vocab vc = make_vocab(E);
+    if ((rc = W.counters.ensure(64))) return rc;
+    {
+        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(maxc, 0, (size_t)Bc * 4, st));
+        const int R = E->fast_R, T = kStageTilesMax;
+        bool need_general = true;
+        if (R > 0) {
+            if ((rc = W.plan.ensure((size_t)Bc * sizeof(StageRec)))) return rc;
+            PlanArgs P;
+            P.s1 = s1; P.s2 = s2; P.p0 = p0; P.npairs = Bc; P.R = R; P.T = T; P._pad = 0;
+            P.rows1 = rows1; P.rows2 = rows2; P.u12 = u12;
+            P.stages = W.plan.as<StageRec>(); P.nstages = W.counters.as<unsigned int>() + 9;
+            const int pblocks = (int)std::min<int64_t>(((int64_t)Bc + 127) / 128, (int64_t)E->sm_count * 16);
+            {
+                Prof pr(E, WMD_K_COST, st);
+                cost_plan_kernel<<<pblocks, 128, 0, st>>>(P);
+                CK(cudaGetLastError());
+            }
+            FastArgs F;
+            F.vc = vc; F.plan = E->plan; F.R = R; F.S = E->fast_S; F.ldr = E->fast_ldr; F.rowbytes = E->ld * 4;
+            F.negzero2 = 0x8000000080000000ull;
+            F.stages = P.stages; F.nstages = P.nstages;
+            F.tiles = tiles; F.tile_stride = tile_stride; F.maxc = maxc;
+            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
+            Prof pr(E, WMD_K_COST, st);
+            if (E->fast_PL == 4) cost_tiles_fast_kernel<4><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            else if (E->fast_PL == 2) cost_tiles_fast_kernel<2><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            else cost_tiles_fast_kernel<1><<<grid, kFastThreads, E->fast_smem, st>>>(F);
+            CK(cudaGetLastError());
+            // every pair of this chunk fits a stage when the longest possible one does
+            const int a = std::min(ml1, ml2), b = std::max(ml1, ml2);
+            const int worst_tiles = std::min(((a + 1) / 2) * ((b + 3) / 4), ((b + 1) / 2) * ((a + 3) / 4));
+            need_general = ml1 + ml2 > R || worst_tiles > T;
+        }
+        if (need_general) {
+            CostArgs A;
+            A.vc = vc; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
+            A.nchunks = E->cost_nchunks; A.pitch = E->cost_pitch; A.fast_R = R; A.fast_T = T; A._pad = 0;
+            memcpy(A.chunks, E->cost_chunks, sizeof A.chunks);
+            A.negzero2 = 0x8000000080000000ull;
+            A.rows1 = rows1; A.rows2 = rows2; A.u12 = u12;
+            A.tiles = tiles; A.tile_stride = tile_stride;
+            A.maxc = maxc;
+            A.counter = W.counters.as<unsigned int>() + 8;
+            const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
+            const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
+            Prof pr(E, WMD_K_COST, st);
+            cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
+            CK(cudaGetLastError());
+        }
+    }
+    return WMD_OK;
+}
+
 // Launch K1..K3 for pairs [p0, p0 + Bc) on stream st. tok caps bound the token slots of the chunk.
 int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2,
               int64_t p0, int32_t Bc, int64_t tokcap1, int64_t tokcap2, int32_t ml1, int32_t ml2,
@@ -274,57 +343,10 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         nbow_pairs_kernel<<<grid, wpb * 32, smem, st>>>(s1, s2, vc, p0, Bc, Lp, pw, O.out, O.status);
         CK(cudaGetLastError());
     }
-    // ---- K2: planned fast path for pairs that fit a stage, general kernel for the rest
-    {
-        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
-        CK(cudaMemsetAsync(W.maxc.p, 0, (size_t)Bc * 4, st));
-        const int R = E->fast_R, T = kStageTilesMax;
-        bool need_general = true;
-        if (R > 0) {
-            if ((rc = W.plan.ensure((size_t)Bc * sizeof(StageRec)))) return rc;
-            PlanArgs P;
-            P.s1 = s1; P.s2 = s2; P.p0 = p0; P.npairs = Bc; P.R = R; P.T = T; P._pad = 0;
-            P.rows1 = pw.rows1; P.rows2 = pw.rows2; P.u12 = pw.u12;
-            P.stages = W.plan.as<StageRec>(); P.nstages = W.counters.as<unsigned int>() + 9;
-            const int pblocks = (int)std::min<int64_t>(((int64_t)Bc + 127) / 128, (int64_t)E->sm_count * 16);
-            {
-                Prof pr(E, WMD_K_COST, st);
-                cost_plan_kernel<<<pblocks, 128, 0, st>>>(P);
-                CK(cudaGetLastError());
-            }
-            FastArgs F;
-            F.vc = vc; F.plan = E->plan; F.R = R; F.S = E->fast_S; F.ldr = E->fast_ldr; F.rowbytes = E->ld * 4;
-            F.negzero2 = 0x8000000080000000ull;
-            F.stages = P.stages; F.nstages = P.nstages;
-            F.tiles = W.tiles.as<float>(); F.tile_stride = tile_stride; F.maxc = W.maxc.as<unsigned int>();
-            const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
-            Prof pr(E, WMD_K_COST, st);
-            if (E->fast_PL == 4) cost_tiles_fast_kernel<4><<<grid, kFastThreads, E->fast_smem, st>>>(F);
-            else if (E->fast_PL == 2) cost_tiles_fast_kernel<2><<<grid, kFastThreads, E->fast_smem, st>>>(F);
-            else cost_tiles_fast_kernel<1><<<grid, kFastThreads, E->fast_smem, st>>>(F);
-            CK(cudaGetLastError());
-            // every pair of this chunk fits a stage when the longest possible one does
-            const int a = std::min(ml1, ml2), b = std::max(ml1, ml2);
-            const int worst_tiles = std::min(((a + 1) / 2) * ((b + 3) / 4), ((b + 1) / 2) * ((a + 3) / 4));
-            need_general = ml1 + ml2 > R || worst_tiles > T;
-        }
-        if (need_general) {
-            CostArgs A;
-            A.vc = vc; A.s1 = s1; A.s2 = s2; A.p0 = p0; A.npairs = Bc;
-            A.nchunks = E->cost_nchunks; A.pitch = E->cost_pitch; A.fast_R = R; A.fast_T = T; A._pad = 0;
-            memcpy(A.chunks, E->cost_chunks, sizeof A.chunks);
-            A.negzero2 = 0x8000000080000000ull;
-            A.rows1 = pw.rows1; A.rows2 = pw.rows2; A.u12 = pw.u12;
-            A.tiles = W.tiles.as<float>(); A.tile_stride = tile_stride;
-            A.maxc = W.maxc.as<unsigned int>();
-            A.counter = W.counters.as<unsigned int>() + 8;
-            const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
-            const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
-            Prof pr(E, WMD_K_COST, st);
-            cost_tiles_kernel<<<grid, kCostThreads, smem, st>>>(A);
-            CK(cudaGetLastError());
-        }
-    }
+    // ---- K2
+    if ((rc = launch_cost(E, W, st, s1, s2, p0, Bc, ml1, ml2, pw.rows1, pw.rows2, pw.u12, W.tiles.as<float>(), tile_stride,
+                          W.maxc.as<unsigned int>())))
+        return rc;
     // ---- K5 (optional)
     if (O.rwmd) {
         RwmdArgs R;
@@ -526,6 +548,241 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     return WMD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// all-pairs mode
+// ------------------------------------------------------------------------------------------------
+enum {
+    AP_IDSA, AP_OFFA, AP_IDSB, AP_OFFB, AP_ROWSA, AP_CNTA, AP_UNIQA, AP_NVALA, AP_ROWSB, AP_CNTB, AP_UNIQB, AP_NVALB,
+    AP_ZB, AP_ZA, AP_LB, AP_KTH, AP_THR, AP_COUNTS, AP_OFFS, AP_CI, AP_CJ, AP_CD, AP_CST, AP_TOPJ, AP_TOPD, AP_KCUR,
+    AP_BIJ, AP_COUNT_
+};
+static_assert(AP_COUNT_ <= 32, "wmd_engine::ap too small");
+
+// D[a][b] for every two table rows, from the K2 kernels run on blocks of consecutive rows.
+int ensure_dtab(wmd_engine *E, cudaStream_t st)
+{
+    if (E->dtab) return WMD_OK;
+    int rc;
+    const int64_t V = E->V;
+    const size_t bytes = (size_t)V * V * 4;
+    size_t freeb = 0, totalb = 0;
+    CK(cudaMemGetInfo(&freeb, &totalb));
+    if (bytes + (4ull << 30) > freeb)
+        return fail(WMD_ENOMEM, "all-pairs mode needs a %lld x %lld float32 distance table (%.1f GB); %.1f GB free",
+                    (long long)V, (long long)V, bytes / 1e9, freeb / 1e9);
+    float *D = nullptr;
+    if (cudaMalloc(&D, bytes) != cudaSuccess) return fail(WMD_ENOMEM, "cudaMalloc(distance table) failed");
+    const int BS = E->fast_R > 0 ? std::min(20, E->fast_R / 2) : 16;
+    const int nb = (int)((V + BS - 1) / BS);
+    const int64_t npairs = (int64_t)nb * (nb + 1) / 2;
+    const int64_t CH = 65536;
+    Workspace &W = E->ws[0];
+    const int64_t tile_stride = (int64_t)BS * BS;
+    if ((rc = W.rows1.ensure((size_t)CH * BS * 4)) || (rc = W.rows2.ensure((size_t)CH * BS * 4)) || (rc = W.u12.ensure((size_t)CH * 4)) ||
+        (rc = W.maxc.ensure((size_t)CH * 4)) || (rc = W.tiles.ensure((size_t)CH * tile_stride * 4)) || (rc = E->ap[AP_BIJ].ensure((size_t)CH * 8))) {
+        cudaFree(D);
+        return rc;
+    }
+    DocSide s1{}, s2{};
+    s1.L = BS; s2.L = BS;                                  // padded layout: work slots at q * BS
+    for (int64_t q0 = 0; q0 < npairs; q0 += CH) {
+        const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - q0);
+        dtab_make_pairs_kernel<<<(Bc + 255) / 256, 256, 0, st>>>((int32_t)V, BS, nb, q0, Bc, W.rows1.as<int32_t>(), W.rows2.as<int32_t>(),
+                                                                 W.u12.as<int32_t>(), E->ap[AP_BIJ].as<int32_t>());
+        if (cudaGetLastError() != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "dtab_make_pairs_kernel launch failed"); }
+        if ((rc = launch_cost(E, W, st, s1, s2, 0, Bc, BS, BS, W.rows1.as<int32_t>(), W.rows2.as<int32_t>(), W.u12.as<int32_t>(),
+                              W.tiles.as<float>(), tile_stride, W.maxc.as<unsigned int>()))) { cudaFree(D); return rc; }
+        dtab_scatter_kernel<<<Bc, 128, 0, st>>>((int32_t)V, BS, Bc, W.u12.as<int32_t>(), E->ap[AP_BIJ].as<int32_t>(), W.tiles.as<float>(),
+                                                tile_stride, D);
+        if (cudaGetLastError() != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "dtab_scatter_kernel launch failed"); }
+    }
+    // largest distance in the table: scales the pruning margin (allpairs.cuh)
+    unsigned int *dmaxbits = W.counters.as<unsigned int>() + 12;
+    if (cudaMemsetAsync(dmaxbits, 0, 4, st) != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "memset failed"); }
+    table_max_kernel<<<E->sm_count * 4, 256, 0, st>>>(D, (int64_t)V * V, dmaxbits);
+    unsigned int hb = 0;
+    if (cudaMemcpyAsync(&hb, dmaxbits, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaFree(D);
+        return fail(WMD_ECUDA, "distance table build failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    memcpy(&E->dmax, &hb, 4);
+    E->dtab = D;
+    return WMD_OK;
+}
+
+// rows / counts / uniq / nval of ndocs documents already on the device
+int ap_nbow(wmd_engine *E, cudaStream_t st, const int32_t *ids_dev, const int64_t *off_dev, int64_t ndocs, int32_t ml, int64_t total,
+            DevBuf &rows, DevBuf &cnt, DevBuf &uniq, DevBuf &nval)
+{
+    int rc;
+    const size_t tb = (size_t)std::max<int64_t>(total, 1);
+    if ((rc = rows.ensure(tb * 4)) || (rc = cnt.ensure(tb * 4)) || (rc = uniq.ensure((size_t)ndocs * 4)) || (rc = nval.ensure((size_t)ndocs * 4)))
+        return rc;
+    DocSide s{};
+    s.ids = ids_dev; s.off = off_dev;
+    const int Lp = std::max(ml, 1);
+    const int wpb = Lp <= 64 ? 8 : 4;
+    const size_t smem = nbow_smem_per_warp(Lp) * wpb;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_docs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((ndocs + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+    Prof pr(E, WMD_K_NBOW, st);
+    nbow_docs_kernel<<<grid, wpb * 32, smem, st>>>(s, make_vocab(E), (int32_t)ndocs, Lp, rows.as<int32_t>(), cnt.as<int32_t>(), nullptr,
+                                                  uniq.as<int32_t>(), nval.as<int32_t>());
+    CK(cudaGetLastError());
+    return WMD_OK;
+}
+
+struct ApTimer {
+    cudaEvent_t a = nullptr, b = nullptr; cudaStream_t st;
+    explicit ApTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~ApTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, st); }
+    double stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float t = 0.f; cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+// exact WMD of the candidate pairs (ci[p] in A, cj[p] in B) -> cd[p]
+int ap_exact(wmd_engine *E, cudaStream_t st, const int32_t *idsA, const int64_t *offA, int32_t mlA, const int32_t *idsB,
+             const int64_t *offB, int32_t mlB, const int32_t *ci, const int32_t *cj, int64_t n, double *cd, int32_t *cst)
+{
+    if (n == 0) return WMD_OK;
+    DocSide s1{}, s2{};
+    s1.ids = idsA; s1.off = offA; s1.sel = ci; s1.slot = std::max(mlA, 1);
+    s2.ids = idsB; s2.off = offB; s2.sel = cj; s2.slot = std::max(mlB, 1);
+    return run_dev_job(E, s1, s2, n * (int64_t)std::max(mlA, 1), n * (int64_t)std::max(mlB, 1), mlA, mlB, n, cd, cst, st);
+}
+
+int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_t nA, const int32_t *idsB, const int64_t *offB, int64_t nB,
+                 int32_t k, int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist, int64_t *stats, double *ms)
+{
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if (nA < 0 || nB < 0 || k <= 0 || row_begin < 0 || row_end > nA || row_begin > row_end) return fail(WMD_EINVAL, "bad all-pairs arguments");
+    if (nA > 0x7fffffff || nB > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
+    if (k > nB) return fail(WMD_EINVAL, "k = %d exceeds the %lld documents of set B", k, (long long)nB);
+    if (k > 1024) return fail(WMD_EINVAL, "k is limited to 1024");
+    const int64_t nR = row_end - row_begin;
+    if (nR == 0) return WMD_OK;
+    if (!offA || !offB || !out_idx || !out_dist) return fail(WMD_EINVAL, "null argument");
+    int32_t mlA = 0, mlB = 0;
+    if ((rc = scan_offsets(offA + row_begin, nR, mlA, "set A"))) return rc;
+    if ((rc = scan_offsets(offB, nB, mlB, "set B"))) return rc;
+    cudaStream_t st = E->ap_stream;
+    DevBuf *B = E->ap;
+    ApTimer tm(st);
+    double ms_local[4] = { 0, 0, 0, 0 };                       // distance table, corpus index (Z_B), bounds + selection, exact solves
+    int64_t st_local[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };          // lb pairs, round-1 solves, round-2 solves, query blocks
+
+    tm.start();
+    if ((rc = ensure_dtab(E, st))) return rc;
+    ms_local[0] = tm.stop();
+
+    // ---- documents to the device; nBOW of both sets ------------------------------------------------
+    tm.start();
+    const int64_t baseA = offA[row_begin], totA = offA[row_end] - baseA, baseB = offB[0], totB = offB[nB] - baseB;
+    if ((totA > 0 && !idsA) || (totB > 0 && !idsB)) return fail(WMD_EINVAL, "null ids");
+    if ((rc = B[AP_IDSA].ensure((size_t)std::max<int64_t>(totA, 1) * 4)) || (rc = B[AP_OFFA].ensure((size_t)(nR + 1) * 8)) ||
+        (rc = B[AP_IDSB].ensure((size_t)std::max<int64_t>(totB, 1) * 4)) || (rc = B[AP_OFFB].ensure((size_t)(nB + 1) * 8)))
+        return rc;
+    if (totA) CK(cudaMemcpyAsync(B[AP_IDSA].p, idsA + baseA, (size_t)totA * 4, cudaMemcpyHostToDevice, st));
+    if (totB) CK(cudaMemcpyAsync(B[AP_IDSB].p, idsB + baseB, (size_t)totB * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[AP_OFFA].p, offA + row_begin, (size_t)(nR + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B[AP_OFFB].p, offB, (size_t)(nB + 1) * 8, cudaMemcpyHostToDevice, st));
+    // offsets stay absolute; rebase the id pointers instead
+    const int32_t *dIdsA = B[AP_IDSA].as<int32_t>() - baseA, *dIdsB = B[AP_IDSB].as<int32_t>() - baseB;
+    const int64_t *dOffA = B[AP_OFFA].as<int64_t>(), *dOffB = B[AP_OFFB].as<int64_t>();
+    if ((rc = ap_nbow(E, st, dIdsA, dOffA, nR, mlA, totA + baseA, B[AP_ROWSA], B[AP_CNTA], B[AP_UNIQA], B[AP_NVALA]))) return rc;
+    if ((rc = ap_nbow(E, st, dIdsB, dOffB, nB, mlB, totB + baseB, B[AP_ROWSB], B[AP_CNTB], B[AP_UNIQB], B[AP_NVALB]))) return rc;
+    // ---- Z_B[w][j] ----------------------------------------------------------------------------------
+    const int64_t ldzb = (nB + 31) & ~31ll;
+    if ((rc = B[AP_ZB].ensure((size_t)E->V * ldzb * 4))) return rc;
+    {
+        ZArgs Z;
+        Z.D = E->dtab; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSB].as<int32_t>(); Z.off = dOffB; Z.uniq = B[AP_UNIQB].as<int32_t>();
+        Z.doc0 = 0; Z.ndocs = (int32_t)nB; Z.Z = B[AP_ZB].as<float>(); Z.ldz = ldzb;
+        dim3 grid((unsigned)((nB + 31) / 32), (unsigned)((E->V + 31) / 32));
+        z_build_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
+        CK(cudaGetLastError());
+    }
+    ms_local[1] = tm.stop();
+
+    // ---- query blocks ---------------------------------------------------------------------------------
+    int64_t IB = std::min<int64_t>(nR, std::max<int64_t>(32, (int64_t)(1ll << 29) / std::max<int64_t>(nB, 1)));
+    IB = std::min<int64_t>(IB, 4096);
+    const int64_t ldza = (IB + 31) & ~31ll, ldlb = ldzb;
+    if ((rc = B[AP_ZA].ensure((size_t)E->V * ldza * 4)) || (rc = B[AP_LB].ensure((size_t)IB * ldlb * 4)) || (rc = B[AP_KTH].ensure((size_t)IB * 4)) ||
+        (rc = B[AP_THR].ensure((size_t)IB * 4)) || (rc = B[AP_COUNTS].ensure((size_t)IB * 4)) || (rc = B[AP_OFFS].ensure((size_t)(IB + 1) * 8)) ||
+        (rc = B[AP_TOPJ].ensure((size_t)IB * k * 4)) || (rc = B[AP_TOPD].ensure((size_t)IB * k * 8)) || (rc = B[AP_KCUR].ensure((size_t)IB * 4)))
+        return rc;
+    for (int64_t i0 = 0; i0 < nR; i0 += IB) {
+        const int32_t ni = (int32_t)std::min<int64_t>(IB, nR - i0);
+        st_local[3] += 1;
+        tm.start();
+        {
+            ZArgs Z;
+            Z.D = E->dtab; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSA].as<int32_t>(); Z.off = dOffA; Z.uniq = B[AP_UNIQA].as<int32_t>();
+            Z.doc0 = i0; Z.ndocs = ni; Z.Z = B[AP_ZA].as<float>(); Z.ldz = ldza;
+            // rows of set A live at their absolute CSR offsets minus baseA: shift the pointer like the ids
+            Z.rows = B[AP_ROWSA].as<int32_t>();
+            dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((E->V + 31) / 32));
+            z_build_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
+            CK(cudaGetLastError());
+            LbArgs L;
+            L.rowsA = B[AP_ROWSA].as<int32_t>(); L.cntA = B[AP_CNTA].as<int32_t>(); L.offA = dOffA; L.uniqA = B[AP_UNIQA].as<int32_t>();
+            L.nvalA = B[AP_NVALA].as<int32_t>(); L.i0 = i0; L.ni = ni;
+            L.rowsB = B[AP_ROWSB].as<int32_t>(); L.cntB = B[AP_CNTB].as<int32_t>(); L.offB = dOffB; L.uniqB = B[AP_UNIQB].as<int32_t>();
+            L.nvalB = B[AP_NVALB].as<int32_t>(); L.nB = (int32_t)nB;
+            L.ZB = B[AP_ZB].as<float>(); L.ldzb = ldzb; L.ZA = B[AP_ZA].as<float>(); L.ldza = ldza;
+            L.LB = B[AP_LB].as<float>(); L.ldlb = ldlb;
+            dim3 g2((unsigned)((nB + 31) / 32), (unsigned)((ni + 31) / 32));
+            lb_tile_kernel<<<g2, dim3(32, 32), 0, st>>>(L);
+            CK(cudaGetLastError());
+            st_local[0] += (int64_t)ni * nB;
+        }
+        CK(cudaMemsetAsync(B[AP_KCUR].p, 0, (size_t)ni * 4, st));
+        row_kth_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, k, B[AP_KTH].as<float>());
+        CK(cudaGetLastError());
+        for (int round = 0; round < 2; ++round) {
+            const float *lo = round == 0 ? nullptr : B[AP_KTH].as<float>();
+            const float *hi = round == 0 ? B[AP_KTH].as<float>() : B[AP_THR].as<float>();
+            cand_rows_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, lo, hi, 0, B[AP_COUNTS].as<int32_t>(), nullptr,
+                                                (int32_t)i0, nullptr, nullptr);
+            CK(cudaGetLastError());
+            scan_counts_kernel<<<1, 1024, 0, st>>>(B[AP_COUNTS].as<int32_t>(), ni, B[AP_OFFS].as<int64_t>());
+            CK(cudaGetLastError());
+            int64_t ncand = 0;
+            CK(cudaMemcpyAsync(&ncand, B[AP_OFFS].as<int64_t>() + ni, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (round == 0) ms_local[2] += tm.stop(); else ms_local[2] += tm.stop();
+            tm.start();
+            if (ncand > 0) {
+                if ((rc = B[AP_CI].ensure((size_t)ncand * 4)) || (rc = B[AP_CJ].ensure((size_t)ncand * 4)) || (rc = B[AP_CD].ensure((size_t)ncand * 8)) ||
+                    (rc = B[AP_CST].ensure((size_t)ncand * 4)))
+                    return rc;
+                cand_rows_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, lo, hi, 1, nullptr, B[AP_OFFS].as<int64_t>(),
+                                                    (int32_t)i0, B[AP_CI].as<int32_t>(), B[AP_CJ].as<int32_t>());
+                CK(cudaGetLastError());
+                if ((rc = ap_exact(E, st, dIdsA, dOffA, mlA, dIdsB, dOffB, mlB, B[AP_CI].as<int32_t>(), B[AP_CJ].as<int32_t>(), ncand,
+                                   B[AP_CD].as<double>(), B[AP_CST].as<int32_t>())))
+                    return rc;
+            }
+            topk_merge_kernel<<<ni, 256, (size_t)k * 12, st>>>(k, B[AP_OFFS].as<int64_t>(), B[AP_CJ].as<int32_t>(), B[AP_CD].as<double>(),
+                                                             B[AP_TOPJ].as<int32_t>(), B[AP_TOPD].as<double>(), B[AP_KCUR].as<int32_t>(),
+                                                             B[AP_THR].as<float>());
+            CK(cudaGetLastError());
+            st_local[1 + round] += ncand;
+            ms_local[3] += tm.stop();
+            tm.start();
+        }
+        CK(cudaMemcpyAsync(out_idx + i0 * k, B[AP_TOPJ].p, (size_t)ni * k * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_dist + i0 * k, B[AP_TOPD].p, (size_t)ni * k * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ms_local[2] += tm.stop();
+    }
+    if (stats) for (int i = 0; i < 8; ++i) stats[i] = st_local[i];
+    if (ms) for (int i = 0; i < 4; ++i) ms[i] = ms_local[i];
+    return WMD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -575,6 +832,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if (cudaEventCreateWithFlags(&E->ev_slot[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(WMD_ECUDA, "event create failed"));
     }
     if (cudaEventCreateWithFlags(&E->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(WMD_ECUDA, "event create failed"));
+    if (cudaStreamCreateWithFlags(&E->ap_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(WMD_ECUDA, "stream create failed"));
     if (cudaMalloc(&E->stats, 6 * sizeof(unsigned long long)) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc failed"));
     cudaMemset(E->stats, 0, 6 * sizeof(unsigned long long));
     if (normalize) {
@@ -598,6 +856,9 @@ int wmd_destroy(wmd_handle E)
         if (E->ev_slot[i]) cudaEventDestroy(E->ev_slot[i]);
     }
     if (E->ev_fork) cudaEventDestroy(E->ev_fork);
+    if (E->dtab) cudaFree(E->dtab);
+    for (auto &b : E->ap) b.release();
+    if (E->ap_stream) cudaStreamDestroy(E->ap_stream);
     if (E->table) cudaFree(E->table);
     if (E->map) cudaFree(E->map);
     if (E->rank) cudaFree(E->rank);
@@ -731,7 +992,7 @@ int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t 
         Prof pr(E, WMD_K_NBOW, st);
         nbow_docs_kernel<<<grid, wpb * 32, smem, st>>>(s, make_vocab(E), (int32_t)ndocs, Lp,
                                                       W.rows1.as<int32_t>() - base, W.cnt1.as<int32_t>() - base,
-                                                      W.pqn.as<double>() - base, W.u12.as<int32_t>());
+                                                      W.pqn.as<double>() - base, W.u12.as<int32_t>(), nullptr);
         CK(cudaGetLastError());
     }
     if (total) {
@@ -742,6 +1003,14 @@ int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t 
     CK(cudaMemcpyAsync(uniq, W.u12.p, (size_t)ndocs * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return WMD_OK;
+}
+
+int wmd_allpairs_topk_host(wmd_handle E, const int32_t *idsA, const int64_t *offA, int64_t nA,
+                           const int32_t *idsB, const int64_t *offB, int64_t nB, int32_t k, int64_t row_begin, int64_t row_end,
+                           int32_t *out_idx, double *out_dist, int64_t *stats, double *ms)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    return run_allpairs(E, idsA, offA, nA, idsB, offB, nB, k, row_begin, row_end, out_idx, out_dist, stats, ms);
 }
 
 int wmd_set_profiling(wmd_handle E, int32_t enabled)

@@ -147,6 +147,26 @@ class WMDEngine:
                                                _ptr(am1, c_i32p), _ptr(am2, c_i32p), _ptr(st, c_i32p)))
         return dict(lb=lb, l1=l1, l2=l2, argmin_rows=am1, argmin_cols=am2, status=st)
 
+    def allpairs_topk(self, idsA, offA, idsB, offB, k: int, row_begin: int = 0, row_end: Optional[int] = None):
+        """For rows [row_begin, row_end) of set A: the k documents of set B with the smallest WMD,
+        ordered by (distance, index).  Returns (idx int32 [rows, k], dist float64 [rows, k], info)."""
+        idsA, idsB = _np(idsA, np.int32), _np(idsB, np.int32)
+        offA, offB = _np(offA, np.int64), _np(offB, np.int64)
+        nA, nB = offA.shape[0] - 1, offB.shape[0] - 1
+        row_end = nA if row_end is None else int(row_end)
+        rows = row_end - int(row_begin)
+        idx = np.empty((max(rows, 0), int(k)), np.int32)
+        dist = np.empty((max(rows, 0), int(k)), np.float64)
+        stats = (ctypes.c_int64 * 8)()
+        ms = (ctypes.c_double * 4)()
+        _lib.check(self._L.wmd_allpairs_topk_host(self._handle(), _ptr(idsA, c_i32p), _ptr(offA, c_i64p), nA,
+                                                  _ptr(idsB, c_i32p), _ptr(offB, c_i64p), nB, int(k), int(row_begin), row_end,
+                                                  _ptr(idx, c_i32p), _ptr(dist, c_f64p), stats, ms))
+        info = {"bounds": int(stats[0]), "exact_round1": int(stats[1]), "exact_round2": int(stats[2]),
+                "query_blocks": int(stats[3]), "ms_dist_table": ms[0], "ms_corpus_index": ms[1],
+                "ms_bounds_select": ms[2], "ms_exact": ms[3]}
+        return idx, dist, info
+
     # -- scoring: device tensors (torch) ----------------------------------------------------
     def wmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, out=None, status=None):
         """CSR pairs in torch CUDA tensors (int32 ids, int64 offsets) -> float64 CUDA tensor.

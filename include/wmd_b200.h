@@ -20,6 +20,8 @@
  *     evaluate/auto/content_preserve.py:43-50 (caller: evaluate/eval.py:42)
  *   gensim nbow() / Dictionary.doc2bow  [third party]            wmd_nbow_host
  *   (not in the reference: Kusner et al. 2015 lower bound)       wmd_rwmd_pairs_host
+ *   (not in the reference: all-pairs top-k with RWMD pruning,    wmd_allpairs_topk_host
+ *    BASELINE.json configs[3])
  *
  * Conventions
  *   - every function returns 0 on success and a negative WMD_E* code on failure; the message
@@ -114,6 +116,22 @@ int wmd_rwmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
                         const int32_t *ids2, const int64_t *off2, int64_t npairs,
                         double *lb, double *l1, double *l2,
                         int32_t *argmin_rows, int32_t *argmin_cols, int32_t *status);
+
+/* All-pairs mode (BASELINE.json configs[3]; not in the reference).  For every document i of set A
+ * in [row_begin, row_end), the k documents j of set B with the smallest WMD(i, j), ordered by
+ * (distance, j); the distances are the same values wmd_pairs_host returns for (A_i, B_j), +inf
+ * included.  Candidates are pruned with the relaxed lower bound (Kusner et al. 2015) evaluated
+ * through a V x V table of word distances and per-corpus word-to-document minima (LC-RWMD, Atasu
+ * et al. 2017); every surviving pair is solved exactly.  out_idx / out_dist are
+ * [(row_end - row_begin), k] HOST arrays.  Row blocks are independent, so ranks of a multi-GPU job
+ * call this with disjoint [row_begin, row_end).
+ * stats[8] (may be NULL): {bounds evaluated, exact solves round 1, exact solves round 2, query
+ * blocks, 0...};  ms[4] (may be NULL): device milliseconds spent on {word-distance table (first
+ * call only), corpus index Z_B + nBOW, bounds + selection, exact solves + merges}. */
+int wmd_allpairs_topk_host(wmd_handle h, const int32_t *idsA, const int64_t *offA, int64_t nA,
+                           const int32_t *idsB, const int64_t *offB, int64_t nB, int32_t k,
+                           int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist,
+                           int64_t *stats, double *ms);
 
 /* instrumentation ----------------------------------------------------------------------------- */
 

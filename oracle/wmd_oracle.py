@@ -293,3 +293,26 @@ def rwmd_pair(table: np.ndarray, doc1_rows: Sequence[int], doc2_rows: Sequence[i
     for j in range(len(r2)):
         l2 += w2[j] * float(D[am_c[j], j])
     return max(l1, l2), l1, l2, am_r, am_c
+
+
+# --------------------------------------------------------------------------- #
+# All-pairs top-k (not in the reference; BASELINE.json configs[3]): brute force.
+# --------------------------------------------------------------------------- #
+def allpairs_topk_bruteforce(table: np.ndarray, idsA, offA, idsB, offB, k: int,
+                             rank: Optional[np.ndarray] = None, nthreads: int = 4):
+    """Every (A_i, B_j) distance with batch_wmd, then the k smallest per row by (distance, j).
+    Returns (idx int32 [nA, k], dist float64 [nA, k]).  Quadratic: small cases only."""
+    idsA = np.ascontiguousarray(idsA, np.int32); idsB = np.ascontiguousarray(idsB, np.int32)
+    offA = np.ascontiguousarray(offA, np.int64); offB = np.ascontiguousarray(offB, np.int64)
+    nA, nB = offA.shape[0] - 1, offB.shape[0] - 1
+    idx = np.empty((nA, k), np.int32); dist = np.empty((nA, k), np.float64)
+    lenB = np.diff(offB)
+    for i in range(nA):
+        doc = idsA[offA[i]:offA[i + 1]]
+        ids1 = np.tile(doc, nB)
+        off1 = np.arange(nB + 1, dtype=np.int64) * len(doc)
+        d, _ = batch_wmd(table, ids1, off1, idsB[offB[0]:offB[nB]], offB - offB[0], rank=rank, nthreads=nthreads)
+        order = np.lexsort((np.arange(nB), d))[:k]             # by distance, then by j (inf sorts last)
+        idx[i] = order; dist[i] = d[order]
+    assert lenB.shape[0] == nB
+    return idx, dist
