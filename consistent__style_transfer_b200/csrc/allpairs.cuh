@@ -142,11 +142,10 @@ lb_tile_kernel(const __grid_constant__ LbArgs A)
                 acc = 0.0;
                 const int64_t a = A.offB[j];
                 const int u = A.uniqB[j];
-                const double dn = (double)n;
-                for (int k = 0; k < u; ++k) {
-                    const double wgt = (double)A.cntB[a + k] / dn;
-                    acc += wgt * (double)A.ZA[(int64_t)A.rowsB[a + k] * A.ldza + i];
-                }
+                const double inv = 1.0 / (double)n;              // bounds only: kLbMargin covers the rounding
+                for (int k = 0; k < u; ++k)
+                    acc += (double)A.cntB[a + k] * (double)A.ZA[(int64_t)A.rowsB[a + k] * A.ldza + i];
+                acc *= inv;
             }
         }
         l2t[y][x] = acc;
@@ -162,29 +161,31 @@ lb_tile_kernel(const __grid_constant__ LbArgs A)
                 acc = 0.0;
                 const int64_t a = A.offA[A.i0 + i];
                 const int u = A.uniqA[A.i0 + i];
-                const double dn = (double)n;
-                for (int k = 0; k < u; ++k) {
-                    const double wgt = (double)A.cntA[a + k] / dn;
-                    acc += wgt * (double)A.ZB[(int64_t)A.rowsA[a + k] * A.ldzb + j];
-                }
+                const double inv = 1.0 / (double)n;
+                for (int k = 0; k < u; ++k)
+                    acc += (double)A.cntA[a + k] * (double)A.ZB[(int64_t)A.rowsA[a + k] * A.ldzb + j];
+                acc *= inv;
             }
             const double l2 = l2t[x][y];
             double lb = acc > l2 ? acc : l2;            // inf if either side is empty
-            // round DOWN to float so that the stored bound never exceeds the FP64 one
-            float f = __double2float_rd(lb);
+            // round DOWN to float (and shave two ulps for the reciprocal weights) so that the stored
+            // bound never exceeds the exact one
+            float f = __double2float_rd(lb * (1.0 - 1e-12));
             A.LB[(int64_t)i * A.ldlb + j] = f;
         }
     }
 }
 
-// ---- per-row k-th smallest of LB (radix select on the float bits; all values are >= 0 or +inf) ----
-__global__ void __launch_bounds__(256)
-row_kth_kernel(const float *LB, int64_t ldlb, int32_t n, int32_t k, float *kth)
+// ---- per-row k-th smallest of LB -------------------------------------------------------------------
+// All values are >= 0 or +inf, so the float bit patterns order like the values.  Common case (k <= 256):
+// every thread keeps the minimum of its strided share; the k-th smallest of those 256 minima, T, is an
+// upper bound of the row's k-th smallest (k different threads hold a value <= T), and the few values
+// <= T are collected and ranked.  A radix select over the bits (4 histogram passes) is the fallback
+// when more than kKthCap values qualify (heavy ties) or k > 256.
+constexpr int kKthCap = 2048;
+
+__device__ void row_kth_radix(const unsigned *row, int32_t n, int32_t k, unsigned *hist, unsigned *s_pk, float *out)
 {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_k;
-    const unsigned *row = reinterpret_cast<const unsigned *>(LB + (int64_t)blockIdx.x * ldlb);
-    if (k > n) { if (threadIdx.x == 0) kth[blockIdx.x] = __int_as_float(0x7f800000); return; }
     unsigned prefix = 0, mask = 0, kk = (unsigned)k;
     for (int shift = 24; shift >= 0; shift -= 8) {
         hist[threadIdx.x] = 0;
@@ -197,14 +198,53 @@ row_kth_kernel(const float *LB, int64_t ldlb, int32_t n, int32_t k, float *kth)
         if (threadIdx.x == 0) {
             unsigned acc = 0, b = 0;
             for (; b < 256; ++b) { if (acc + hist[b] >= kk) break; acc += hist[b]; }
-            s_prefix = prefix | (b << shift);
-            s_k = kk - acc;
+            s_pk[0] = prefix | (b << shift);
+            s_pk[1] = kk - acc;
         }
         __syncthreads();
-        prefix = s_prefix; kk = s_k; mask |= 0xffu << shift;
+        prefix = s_pk[0]; kk = s_pk[1]; mask |= 0xffu << shift;
         __syncthreads();
     }
-    if (threadIdx.x == 0) kth[blockIdx.x] = __uint_as_float(prefix);
+    if (threadIdx.x == 0) *out = __uint_as_float(prefix);
+}
+
+__global__ void __launch_bounds__(256)
+row_kth_kernel(const float *LB, int64_t ldlb, int32_t n, int32_t k, float *kth)
+{
+    __shared__ unsigned s_min[256];
+    __shared__ unsigned s_list[kKthCap];
+    __shared__ unsigned s_T, s_cnt, s_pk[2];
+    const unsigned *row = reinterpret_cast<const unsigned *>(LB + (int64_t)blockIdx.x * ldlb);
+    if (k > n) { if (threadIdx.x == 0) kth[blockIdx.x] = __int_as_float(0x7f800000); return; }
+    if (k <= 256 && n >= 256) {
+        unsigned m = 0xffffffffu;
+        for (int j = threadIdx.x; j < n; j += 256) m = min(m, row[j]);
+        s_min[threadIdx.x] = m;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        int rank = 0;
+        for (int t = 0; t < 256; ++t) { const unsigned o = s_min[t]; rank += (o < m) || (o == m && t < (int)threadIdx.x); }
+        if (rank == k - 1) s_T = m;
+        __syncthreads();
+        const unsigned T = s_T;
+        for (int j = threadIdx.x; j < n; j += 256) {
+            const unsigned v = row[j];
+            if (v <= T) { const unsigned pos = atomicAdd(&s_cnt, 1u); if (pos < kKthCap) s_list[pos] = v; }
+        }
+        __syncthreads();
+        const unsigned cnt = s_cnt;
+        if (cnt <= kKthCap) {
+            for (unsigned a = threadIdx.x; a < cnt; a += 256) {
+                const unsigned v = s_list[a];
+                unsigned r = 0;
+                for (unsigned b = 0; b < cnt; ++b) { const unsigned o = s_list[b]; r += (o < v) || (o == v && b < a); }
+                if (r == (unsigned)(k - 1)) kth[blockIdx.x] = __uint_as_float(v);
+            }
+            return;
+        }
+        __syncthreads();
+    }
+    row_kth_radix(row, n, k, s_min, s_pk, kth + blockIdx.x);
 }
 
 // ---- candidate lists: j with lo_i < LB(i, j) <= hi_i, ascending j ---------------------------------

@@ -41,6 +41,24 @@ def test_allpairs_topk_matches_bruteforce(oracle, d):
     eng.close()
 
 
+def test_allpairs_wide_corpus_fast_selection(oracle):
+    """|B| >= 256 takes the two-pass k-th selection (thread minima + ranked short list); heavy ties in the
+    bound (many identical documents) take the radix fallback."""
+    from consistent__style_transfer_b200.engine import WMDEngine
+    V = 500
+    table = workload.make_table(V, 32, seed=4)
+    idsA, offA, idsB, offB = workload.make_pairs(330, "yelp", "independent", V=V, seed=17)
+    idsA, offA = idsA[:offA[60]], offA[:61]
+    eng = WMDEngine(table)
+    _check(table, (idsA, offA), (idsB, offB), 7, oracle, eng)
+    # 2100 copies of three documents: thousands of bounds tie at the k-th value
+    docs = [[1, 2, 3], [4, 5], [6]] * 700 + [[7, 8, 9, 10]] * 3
+    ids, off = workload.to_csr(docs)
+    qa, qo = workload.to_csr([[1, 2, 3], [4, 6], [7, 8, 9, 10], [11]])
+    _check(table, (qa, qo), (ids, off), 5, oracle, eng)
+    eng.close()
+
+
 def test_allpairs_self_join_duplicates_oov_and_empty_docs(oracle):
     """A == B with duplicated documents (zero distances, index tie-breaks), out-of-vocabulary ids and
     documents that are empty after OOV removal (+inf against everything)."""
