@@ -23,6 +23,7 @@
 #include "solve.cuh"
 #include "rwmd.cuh"
 #include "allpairs.cuh"
+#include "emd.cuh"
 
 using namespace wmd;
 
@@ -1011,6 +1012,45 @@ int wmd_allpairs_topk_host(wmd_handle E, const int32_t *idsA, const int64_t *off
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
     return run_allpairs(E, idsA, offA, nA, idsB, offB, nB, k, row_begin, row_end, out_idx, out_dist, stats, ms);
+}
+
+int wmd_emd_batch_host(wmd_handle E, const double *P, const double *Q, const double *D, int64_t nprob, int32_t n,
+                       int32_t shared_d, double extra_mass_penalty, double *out)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (nprob < 0 || n <= 0) return fail(WMD_EINVAL, "bad sizes");
+    if (n > kEmdMaxBins) return fail(WMD_EINVAL, "histograms of %d bins: the limit is %d", n, kEmdMaxBins);
+    if (nprob == 0) return WMD_OK;
+    if (!P || !Q || !D || !out) return fail(WMD_EINVAL, "null argument");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    cudaStream_t st = E->ap_stream;
+    DevBuf *B = E->ap;
+    const int64_t CH = 1 << 20;                                        // problems per launch
+    const size_t dsz = (size_t)n * n * 8;
+    for (int64_t p0 = 0; p0 < nprob; p0 += CH) {
+        const int64_t nb = std::min<int64_t>(CH, nprob - p0);
+        if ((rc = B[AP_IDSA].ensure((size_t)nb * n * 8)) || (rc = B[AP_IDSB].ensure((size_t)nb * n * 8)) ||
+            (rc = B[AP_ZA].ensure(shared_d ? dsz : (size_t)nb * dsz)) || (rc = B[AP_CD].ensure((size_t)nb * 8)))
+            return rc;
+        CK(cudaMemcpyAsync(B[AP_IDSA].p, P + p0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B[AP_IDSB].p, Q + p0 * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(B[AP_ZA].p, shared_d ? D : D + p0 * (int64_t)n * n, shared_d ? dsz : (size_t)nb * dsz, cudaMemcpyHostToDevice, st));
+        EmdArgs A;
+        A.P = B[AP_IDSA].as<double>(); A.Q = B[AP_IDSB].as<double>(); A.D = B[AP_ZA].as<double>();
+        A.nprob = nb; A.n = n; A.shared_d = shared_d; A.extra_mass_penalty = extra_mass_penalty; A.out = B[AP_CD].as<double>();
+        const int wpb = 4;
+        const size_t smem = emd_smem_per_warp(n) * wpb;
+        const int grid = (int)std::min<int64_t>((nb + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+        {
+            Prof pr(E, WMD_K_SOLVE, st);
+            emd_hat_batch_kernel<<<grid, wpb * 32, smem, st>>>(A);
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(out + p0, B[AP_CD].p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return WMD_OK;
 }
 
 int wmd_set_profiling(wmd_handle E, int32_t enabled)

@@ -147,6 +147,20 @@ class WMDEngine:
                                                _ptr(am1, c_i32p), _ptr(am2, c_i32p), _ptr(st, c_i32p)))
         return dict(lb=lb, l1=l1, l2=l2, argmin_rows=am1, argmin_cols=am2, status=st)
 
+    def emd_batch(self, P, Q, D, extra_mass_penalty: float = -1.0) -> np.ndarray:
+        """pyemd.emd for a batch: P, Q float64 [B, n]; D float64 [n, n] (shared) or [B, n, n]."""
+        P, Q, D = _np(P, np.float64), _np(Q, np.float64), _np(D, np.float64)
+        if P.ndim != 2 or P.shape != Q.shape:
+            raise ValueError("P and Q must both be [B, n]")
+        B, n = P.shape
+        shared = D.ndim == 2
+        if D.shape != ((n, n) if shared else (B, n, n)):
+            raise ValueError("D must be [n, n] or [B, n, n]")
+        out = np.empty(B, np.float64)
+        _lib.check(self._L.wmd_emd_batch_host(self._handle(), _ptr(P, c_f64p), _ptr(Q, c_f64p), _ptr(D, c_f64p), B, n,
+                                              int(shared), float(extra_mass_penalty), _ptr(out, c_f64p)))
+        return out
+
     def allpairs_topk(self, idsA, offA, idsB, offB, k: int, row_begin: int = 0, row_end: Optional[int] = None):
         """For rows [row_begin, row_end) of set A: the k documents of set B with the smallest WMD,
         ordered by (distance, index).  Returns (idx int32 [rows, k], dist float64 [rows, k], info)."""

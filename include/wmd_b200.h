@@ -19,6 +19,8 @@
  *   calculate_wmd_scores (per-pair loop)                         wmd_pairs_host
  *     evaluate/auto/content_preserve.py:43-50 (caller: evaluate/eval.py:42)
  *   gensim nbow() / Dictionary.doc2bow  [third party]            wmd_nbow_host
+ *   pyemd.emd(p, q, distance_matrix) called directly             wmd_emd_batch_host
+ *     evaluate/auto/transfer_intensity.py:8-11 (calculate_emd)
  *   (not in the reference: Kusner et al. 2015 lower bound)       wmd_rwmd_pairs_host
  *   (not in the reference: all-pairs top-k with RWMD pruning,    wmd_allpairs_topk_host
  *    BASELINE.json configs[3])
@@ -116,6 +118,15 @@ int wmd_rwmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
                         const int32_t *ids2, const int64_t *off2, int64_t npairs,
                         double *lb, double *l1, double *l2,
                         int32_t *argmin_rows, int32_t *argmin_cols, int32_t *status);
+
+/* pyemd.emd(first_histogram, second_histogram, distance_matrix, extra_mass_penalty) for nprob
+ * independent problems of n <= 31 bins each: P, Q are [nprob, n] float64 HOST arrays, D is one
+ * [n, n] matrix shared by every problem (shared_d != 0) or [nprob, n, n].  Same arithmetic as the
+ * WMD path (emd_hat_gd_metric<double>: bin-wise cancellation, 1e6-grid quantisation, exact integer
+ * optimum, un-normalisation); extra_mass_penalty = -1 means max(D), as in pyemd.  Preconditions as
+ * upstream: non-negative entries, a positive total mass and a positive max(D). */
+int wmd_emd_batch_host(wmd_handle h, const double *P, const double *Q, const double *D, int64_t nprob,
+                       int32_t n, int32_t shared_d, double extra_mass_penalty, double *out);
 
 /* All-pairs mode (BASELINE.json configs[3]; not in the reference).  For every document i of set A
  * in [row_begin, row_end), the k documents j of set B with the smallest WMD(i, j), ordered by
