@@ -143,5 +143,38 @@ def main():
               "zeros", int((v == 0).sum()), "V", len(c["vocab"]))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--noise" not in sys.argv:
     main()
+
+
+def make_noise_cases():
+    """Runs the REFERENCE's own transfer_noise / rand_perm / align (src/data_util.py, executed from
+    where it lies; its one numpy >= 1.24 incompatibility, `np.float`, is aliased to the builtin it
+    meant) on seeded batches of shipped sentences encoded as word ids, and freezes inputs + outputs."""
+    import random
+    src = open(os.path.join(REF, "src/data_util.py"), encoding="utf-8").read()
+    if not hasattr(np, "float"):
+        np.float = float
+    ns = {}
+    exec(compile(src, "reference:src/data_util.py", "exec"), ns)
+    lines = read_lines("data/yelp/style.dev.0")[:600] + read_lines("data/book/style.dev.0")[:300]
+    vocab = {}
+    sents = [[vocab.setdefault(w, len(vocab) + 4) for w in line.split()][:30] for line in lines if line.strip()]
+    cases = []
+    for k, (lo, hi, seed) in enumerate([(0, 256, 11), (256, 512, 12), (600, 728, 13), (40, 41, 14), (100, 103, 15)]):
+        batch = [list(s) for s in sents[lo:hi]]
+        np.random.seed(seed); random.seed(seed + 1000)
+        n1 = ns["transfer_noise"]([list(s) for s in batch], p=0.15)
+        n2 = ns["transfer_noise"]([list(s) for s in batch], p=0.15)
+        n3 = ns["rand_perm"]([list(s) for s in batch], p=0.15)
+        al, lens, ml = ns["align"]([list(s) for s in n1], 0)
+        cases.append({"seed": seed, "batch": batch, "noise1": [[int(t) for t in s] for s in n1],
+                      "noise2": [[int(t) for t in s] for s in n2], "perm": [[int(t) for t in s] for s in n3],
+                      "aligned1": al, "lengths1": lens, "max_len1": ml})
+    with gzip.open(os.path.join(HERE, "noise_cases.json.gz"), "wt", encoding="utf-8") as f:
+        json.dump(cases, f)
+    print("noise cases:", len(cases))
+
+
+if __name__ == "__main__" and "--noise" in sys.argv:
+    make_noise_cases()

@@ -33,3 +33,8 @@ def same_floats(a, b):
     """bit-exact equality of two float64 arrays (inf == inf, 0.0 == 0.0)."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+def noise_cases():
+    with gzip.open(os.path.join(GOLDEN, "noise_cases.json.gz"), "rt", encoding="utf-8") as f:
+        return json.load(f)

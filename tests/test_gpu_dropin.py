@@ -117,3 +117,37 @@ def test_non_lazy_constructor_is_loud_without_gensim():
         pass
     with pytest.raises(RuntimeError, match="gensim"):
         WMDdistance(["nope.txt"], None)
+
+
+def test_collate_pretrain_matches_reference_pipeline(oracle, cases):
+    """src/loader.py:46-70 end to end: the reference's noising (frozen from its own source in
+    tests/golden/noise_cases.json.gz) + the batched WMD label against the oracle's per-pair loop."""
+    import random
+
+    import torch
+    from golden_util import noise_cases
+    from consistent__style_transfer_b200.loader import collate_pretrain
+    from consistent__style_transfer_b200.wmd import WMDdistance
+    c = cases[0]
+    w = WMDdistance.from_embeddings(c["vocab"], c["raw_vectors"], normalize=True)
+    V = len(c["vocab"])
+    toks = ["<pad>", "<s>", "</s>", "<unk>"] + list(c["vocab"])
+    bpe = FakeBPE(toks)
+    kv = oracle.KeyedVectorsOracle(c["vocab"], c["raw_vectors"], normalize=True)
+    ow = oracle.WMDdistanceOracle(kv)
+    for nc in noise_cases()[:3]:
+        # golden batches hold ids >= 4 from a larger word list: fold them into this table's id range
+        batch = [[4 + (t % V) for t in s] for s in nc["batch"]]
+        samples = [(s, i % 2) for i, s in enumerate(batch)]
+        np.random.seed(nc["seed"]); random.seed(nc["seed"] + 1000)
+        out = collate_pretrain(bpe, w)(samples)
+        assert len(out) == 6 and [t.dtype for t in out] == [torch.long] * 5 + [torch.float32]
+        # replay the same draws to recover the noised sentences the labels were computed on
+        from consistent__style_transfer_b200 import data_util
+        np.random.seed(nc["seed"]); random.seed(nc["seed"] + 1000)
+        n1 = data_util.transfer_noise([list(s) for s in batch], p=0.15)
+        n2 = data_util.transfer_noise([list(s) for s in batch], p=0.15)
+        want = ow.cal_wmd_label(n1, n2, bpe)
+        assert out[5].numpy().tobytes() == np.asarray(want, np.float32).tobytes()
+        assert out[0].shape[0] == len(batch) and out[1].shape[0] == len(batch)
+        assert out[4].tolist() == [i % 2 for i in range(len(batch))]
