@@ -203,7 +203,21 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
                 jl = __ffs(__ballot_sync(kFull, key == delta)) - 1;
                 used |= 1u << jl;
                 def = __shfl_sync(kFull, deficit, jl);
-                if (def > 0) break;
+                if (def > 0) {
+                    // A deficit column reached straight from the root row: ship along the single arc (r, jl)
+                    // and, if the row still holds supply, KEEP the search going -- only a forward arc out of
+                    // the root changed, every label stays a feasible potential, and jl (now saturated) is
+                    // expanded like any other saturated column.  Restarting here re-selected all the columns
+                    // this row had already filled.  Longer paths change reverse arcs the tree rests on: those
+                    // leave the loop and restart the search after the augmentation.
+                    if (__shfl_sync(kFull, way, jl) != r) break;
+                    const int amt = min(sup, def);
+                    if (lane == jl) { flow[r * ldc + jl] += amt; colmask |= 1u << r; deficit -= amt; }
+                    __syncwarp();
+                    sup -= amt;
+                    def -= amt;
+                    if (sup == 0) break;                         // def may be > 0: the standard end of a search
+                }
                 unsigned nr = __shfl_sync(kFull, colmask, jl) & ~tree;   // rows shipping into the saturated column
                 tree |= nr;
                 if ((nr >> lane) & 1u) { rdist = delta; rpred = jl; }
@@ -219,6 +233,7 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
             }
             if ((tree >> lane) & 1u) u += delta - rdist;         // dual update (tree nodes only)
             if ((used >> lane) & 1u) v -= delta - minv;
+            if (sup == 0) { __syncwarp(); break; }               // the row emptied on a direct arc
             int amt = min(sup, def);
             for (int j = jl;;) {                                 // bottleneck along the tree path jl -> r
                 const int i = __shfl_sync(kFull, way, j);
