@@ -222,11 +222,23 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
         const float o = __shfl_xor_sync(kFull, theirs, 1);
         res[j] = __fadd_rn(mine, o);                               // (r0+r1+r2+r3) + (r4+..+r7); fadd commutes
     }
-    for (int t = eend; t < start + len; ++t) {                     // the len % 8 tail, sequential, kept cells only
+    const int tail = len & 7;                                      // the len % 8 tail: sequential adds, kept cells only
+    if (tail == 4) {                                               // d = 100, 300, ...: one quad per row, packed sub / square
+        const Q4 x0 = ldq(a[0] + eend), x1 = ldq(a[1] + eend), y0 = ldq(bk[0] + eend), y1 = ldq(bk[1] + eend);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float s = __fsub_rn(a[j >> 1][t], bk[j & 1][t]);
-            res[j] = __fadd_rn(res[j], __fmul_rn(s, s));
+            const Q4 &x = (j >> 1) ? x1 : x0;
+            const Q4 &y = (j & 1) ? y1 : y0;
+            const f32x2 lo = sq2(sub2(x.lo, y.lo), nz), hi = sq2(sub2(x.hi, y.hi), nz);
+            res[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(res[j], lo_f(lo)), hi_f(lo)), lo_f(hi)), hi_f(hi));
+        }
+    } else {
+        for (int t = eend; t < start + len; ++t) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float s = __fsub_rn(a[j >> 1][t], bk[j & 1][t]);
+                res[j] = __fadd_rn(res[j], __fmul_rn(s, s));
+            }
         }
     }
 }
@@ -346,11 +358,11 @@ cost_tiles_fast_kernel(const __grid_constant__ FastArgs A)
     if (warp < kFastProducers) {
         // ------------------------------ producers ------------------------------
         if (warp >= P) return;
+        int s = warp % S;                                          // slot and use count of stage `it`, kept incrementally
+        uint32_t ph = (uint32_t)(warp / S) & 1u;
         for (int it = warp;; it += P) {
             const int idx = (int)blockIdx.x + it * (int)gridDim.x;
             if (idx >= nst) break;
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
             const StageRec *G = A.stages + idx;
             const int nrows = G->nrows, ntiles = G->ntiles;
             const int row0 = lane < nrows ? G->rows[lane] : 0;
@@ -372,27 +384,34 @@ cost_tiles_fast_kernel(const __grid_constant__ FastArgs A)
                 tma_row_g2s(rows_u32 + (uint32_t)(lane + 32) * pitch, A.vc.table + (int64_t)row1 * A.vc.ld, (uint32_t)A.rowbytes, &full_bar[s]);
             if (lane + 64 < nrows)
                 tma_row_g2s(rows_u32 + (uint32_t)(lane + 64) * pitch, A.vc.table + (int64_t)row2 * A.vc.ld, (uint32_t)A.rowbytes, &full_bar[s]);
+            s += P;
+            while (s >= S) { s -= S; ph ^= 1u; }
         }
     } else {
         // ------------------------------ consumers ------------------------------
         constexpr int TPW = 32 / (2 * PL);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0;; ++it) {
             const int idx = (int)blockIdx.x + it * (int)gridDim.x;
             if (idx >= nst) break;
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
             mbar_wait(&full_bar[s], ph);
             const int ntiles = s_ntiles[s];
             const unsigned char *base = smem_raw + (size_t)s * stage_bytes;
-            for (;;) {
-                int t0 = 0;
-                if (lane == 0) t0 = atomicAdd(&s_taskctr[s], TPW);
-                t0 = __shfl_sync(kFull, t0, 0);
-                if (t0 >= ntiles) break;
+            // the next batch is claimed before the current one runs, so the shared-memory atomic and the
+            // broadcast are off the critical path (a consumer over-claims once per stage: harmless)
+            int t0 = 0;
+            if (lane == 0) t0 = atomicAdd(&s_taskctr[s], TPW);
+            t0 = __shfl_sync(kFull, t0, 0);
+            while (t0 < ntiles) {
+                int tn = 0;
+                if (lane == 0) tn = atomicAdd(&s_taskctr[s], TPW);
                 run_desc_batch<PL>(A, base, ntiles, t0);
+                t0 = __shfl_sync(kFull, tn, 0);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
     }
 }
