@@ -150,6 +150,8 @@ struct FastArgs {
     int32_t S;                         // ring depth (2..kFastMaxStages)
     int32_t ldr;                       // floats between staged rows (ldr / 4 odd: conflict-free LDS.128)
     int32_t rowbytes;                  // bytes copied per row (ld * 4, multiple of 16)
+    int32_t common_iters;              // PL > 1: 8-float iterations of the shortest parallel leaf (lockstep part of the loop)
+    int32_t _pad;
     unsigned long long negzero2;
     const StageRec *stages;
     const unsigned int *nstages;
@@ -166,7 +168,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 // One leaf block [start, start + len) of numpy's pairwise sum for the 2x4 cells (a_r, b_c), c = 4r + cc.
 // half selects accumulators r[0..3] or r[4..7]; the two lanes of a pair meet in a reduce-scatter:
 // afterwards lane `half` holds the four cells c = 2j + half (j = 0..3) in res[j], tail included.
-__device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float *const (&b)[4], int start, int len,
+// `common` (warp-uniform, >= 1) is the number of 8-float iterations every lane of the warp runs in
+// lockstep; a lane whose leaf is longer finishes its extra iterations afterwards.  Lanes that run ahead
+// of their neighbours (as the compiler's own unroll-remainder placement made the 84-float leaf do) shift
+// their 32-byte window onto another leaf's banks: ncu showed 8 wavefronts per LDS.128 instead of 4.
+__device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float *const (&b)[4], int start, int len, int common,
                                          int half, f32x2 nz, float (&res)[4])
 {
     const float *bk[2] = { half ? b[1] : b[0], half ? b[3] : b[2] };      // columns of the kept cells: half, 2 + half
@@ -200,8 +206,24 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
                 acc[r * 4 + c].hi = sq2(sub2(x[r].hi, y[c].hi), nz);
             }
     }
+    e += 8;
 #pragma unroll 2
-    for (e += 8; e < eend; e += 8) {
+    for (int it = 1; it < common; ++it, e += 8) {                 // uniform trip count: the warp stays in lockstep
+        Q4 x[2], y[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y[c] = ldq(b[c] + e);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[r * 4 + c].lo = add2(acc[r * 4 + c].lo, sq2(sub2(x[r].lo, y[c].lo), nz));
+                acc[r * 4 + c].hi = add2(acc[r * 4 + c].hi, sq2(sub2(x[r].hi, y[c].hi), nz));
+            }
+    }
+#pragma unroll 1
+    for (; e < eend; e += 8) {                                     // the longer leaves' extra iterations
         Q4 x[2], y[4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) x[r] = ldq(a[r] + e);
@@ -248,7 +270,7 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
 // pair l and the tree is closed by further reduce-scatter steps, leaving 2 / 1 cells per lane.
 // out[k] is cell cell0 + k * cstep of the tile.
 template <int PL>
-__device__ __forceinline__ void dist_2x4(const SumPlan &plan, f32x2 nz, const float *const (&a)[2], const float *const (&b)[4],
+__device__ __forceinline__ void dist_2x4(const SumPlan &plan, int common, f32x2 nz, const float *const (&a)[2], const float *const (&b)[4],
                                          int sub, float (&out)[4 / PL], int &cell0, int &cstep)
 {
     const int half = sub & 1;
@@ -257,7 +279,7 @@ __device__ __forceinline__ void dist_2x4(const SumPlan &plan, f32x2 nz, const fl
         int sp = 0;
         for (int o = 0; o < plan.nops; ++o) {
             float r[4];
-            leaf_2x4(a, b, plan.start[o], plan.len[o], half, nz, r);
+            leaf_2x4(a, b, plan.start[o], plan.len[o], plan.len[o] >> 3, half, nz, r);
 #pragma unroll
             for (int c = 0; c < 4; ++c) st[sp][c] = r[c];
             ++sp;
@@ -273,7 +295,7 @@ __device__ __forceinline__ void dist_2x4(const SumPlan &plan, f32x2 nz, const fl
     } else {
         const int l = sub >> 1, l0 = l & 1;
         float r[4];
-        leaf_2x4(a, b, plan.start[l], plan.len[l], half, nz, r);
+        leaf_2x4(a, b, plan.start[l], plan.len[l], common, half, nz, r);
         float k2[2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {                              // L0 + L1 (and L2 + L3): keep cells with bit 1 == l0
@@ -313,7 +335,7 @@ __device__ __forceinline__ void run_desc_batch(const FastArgs &A, const unsigned
     const int na = (w.y >> 16) & 0xff, nb = w.y >> 24;
     float v[4 / PL];
     int cell0, cstep;
-    dist_2x4<PL>(A.plan, A.negzero2, a, b, sub, v, cell0, cstep);
+    dist_2x4<PL>(A.plan, A.common_iters, A.negzero2, a, b, sub, v, cell0, cstep);
     float mx = 0.f;
     const unsigned q = w.w & 0xffffu;
     if (live) {

@@ -29,7 +29,7 @@ struct EmdArgs {
     double *out;                         // [nprob]
 };
 
-__host__ __device__ inline size_t emd_smem_per_warp(int n) { return ((size_t)2 * n * (n + 1) + 2 * 32) * 4; }
+__host__ __device__ inline size_t emd_smem_per_warp(int n) { return ((size_t)2 * n * (n + 1) + 3 * 32) * 4; }
 
 __global__ void __launch_bounds__(128)
 emd_hat_batch_kernel(const __grid_constant__ EmdArgs A)
@@ -41,6 +41,7 @@ emd_hat_batch_kernel(const __grid_constant__ EmdArgs A)
     int *flow = cost + n * ldc;
     int *sridx = flow + n * ldc;
     int *scidx = sridx + 32;
+    unsigned *cmask = reinterpret_cast<unsigned *>(scidx + 32);
     for (int64_t pr = (int64_t)blockIdx.x * wpb + wib; pr < A.nprob; pr += (int64_t)gridDim.x * wpb) {
         const double *D = A.D + (A.shared_d ? 0 : pr * (int64_t)n * n);
         const double p = lane < n ? A.P[pr * n + lane] : 0.0;
@@ -90,7 +91,7 @@ emd_hat_batch_kernel(const __grid_constant__ EmdArgs A)
                 if (lane < nc) cost[rI * ldc + lane] = ic;
             }
             __syncwarp();
-            opt = transport_solve_small(m, nc, ldc, cost, flow, supply, deficit, lane);
+            opt = transport_solve_small(m, nc, ldc, cost, flow, cmask, supply, deficit, lane);
         }
         if (lane == 0) {
             double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;

@@ -165,24 +165,25 @@ __device__ long long transport_solve(int m, int nc, int ldc, const int *cost, in
 // ------------------------------------------------------------------------------------------------
 // Class A (m <= 32 rows, nc <= 32 columns incl. the dummy): the same primal-dual method with the
 // whole dual / tree state in registers.  Lane L is both row L and column L:
-//   as a column: potential v, remaining deficit, tentative distance minv, tree predecessor way,
-//                colmask = bitmask of rows currently shipping into this column
+//   as a column: potential v, remaining deficit, tentative distance minv, tree predecessor way
 //   as a row:    potential u, tree distance rdist, predecessor column rpred
-// The tree and the used-column set are warp-uniform bitmasks, so "which rows join the tree when
-// column j saturates" is one shuffle of colmask instead of a scan of the flow matrix.  Only the
-// dense int32 cost and flow matrices live in shared memory.
+// The tree and the used-column set are warp-uniform bitmasks, and cmask[j] (shared memory) is the
+// bitmask of rows currently shipping into column j, so "which rows join the tree when column j
+// saturates" is one broadcast load instead of a scan of the flow matrix.  An augmenting path is
+// walked ONCE with shuffles, hop k landing in lane k; bottleneck (REDUX.MIN) and push then run in
+// parallel over the hops.  Only the dense int32 cost and flow matrices and cmask live in shared memory.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t solve_small_smem_per_warp(int mr, int mc, int ldc)
 {
-    return ((size_t)2 * mr * ldc + mr + mc) * 4;
+    return ((size_t)2 * mr * ldc + mr + mc + 32) * 4;
 }
 
-__device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost, int *flow,
+__device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost, int *flow, unsigned *cmask,
                                                            int supply, int deficit, int lane)
 {
     int u = 0, v = 0;
-    unsigned colmask = 0;
     for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0;
+    cmask[lane] = 0;
     __syncwarp();
     const bool iscol = lane < nc;
     for (int r = 0; r < m; ++r) {
@@ -212,13 +213,13 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
                     // leave the loop and restart the search after the augmentation.
                     if (__shfl_sync(kFull, way, jl) != r) break;
                     const int amt = min(sup, def);
-                    if (lane == jl) { flow[r * ldc + jl] += amt; colmask |= 1u << r; deficit -= amt; }
+                    if (lane == jl) { flow[r * ldc + jl] += amt; cmask[jl] |= 1u << r; deficit -= amt; }
                     __syncwarp();
                     sup -= amt;
                     def -= amt;
                     if (sup == 0) break;                         // def may be > 0: the standard end of a search
                 }
-                unsigned nr = __shfl_sync(kFull, colmask, jl) & ~tree;   // rows shipping into the saturated column
+                unsigned nr = cmask[jl] & ~tree;                 // rows shipping into the saturated column
                 tree |= nr;
                 if ((nr >> lane) & 1u) { rdist = delta; rpred = jl; }
                 while (nr) {
@@ -233,26 +234,27 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
             }
             if ((tree >> lane) & 1u) u += delta - rdist;         // dual update (tree nodes only)
             if ((used >> lane) & 1u) v -= delta - minv;
-            if (sup == 0) { __syncwarp(); break; }               // the row emptied on a direct arc
-            int amt = min(sup, def);
-            for (int j = jl;;) {                                 // bottleneck along the tree path jl -> r
+            if (sup == 0) break;                                 // the row emptied on a direct arc
+            // tree path jl -> ... -> r, walked once: hop k = (row pi ships into column pj, and stops shipping
+            // amt into its tree predecessor column pjp) lands in lane k
+            int pi = 0, pj = 0, pjp = -1, nh = 0;
+            for (int j = jl;; ++nh) {
                 const int i = __shfl_sync(kFull, way, j);
-                if (i == r) break;
-                const int jp = __shfl_sync(kFull, rpred, i);
-                amt = min(amt, flow[i * ldc + jp]);
+                const int jp = __shfl_sync(kFull, rpred, i);     // -1 for the root row
+                if (lane == nh) { pi = i; pj = j; pjp = i == r ? -1 : jp; }
+                if (i == r) { ++nh; break; }
                 j = jp;
             }
-            for (int j = jl;;) {                                 // push amt; each column's lane owns its flow entries
-                const int i = __shfl_sync(kFull, way, j);
-                if (lane == j) { flow[i * ldc + j] += amt; colmask |= 1u << i; }
-                if (i == r) break;
-                const int jp = __shfl_sync(kFull, rpred, i);
-                if (lane == jp) {
-                    const int f = flow[i * ldc + jp] - amt;
-                    flow[i * ldc + jp] = f;
-                    if (f == 0) colmask &= ~(1u << i);
+            const bool hop = lane < nh;
+            const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
+            const int amt = min(min(sup, def), __reduce_min_sync(kFull, frev));
+            if (hop) {
+                flow[pi * ldc + pj] += amt;
+                atomicOr(&cmask[pj], 1u << pi);
+                if (pjp >= 0) {
+                    flow[pi * ldc + pjp] = frev - amt;
+                    if (frev == amt) atomicAnd(&cmask[pjp], ~(1u << pi));
                 }
-                j = jp;
             }
             __syncwarp();
             sup -= amt;
@@ -275,6 +277,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
     int *flow = cost + A.mr * ldc;
     int *sridx = flow + A.mr * ldc;
     int *scidx = sridx + A.mr;
+    unsigned *cmask = reinterpret_cast<unsigned *>(scidx + A.mc);
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
@@ -343,7 +346,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
                     if (lane < nc) cost[rI * ldc + lane] = ic;
                 }
                 __syncwarp();
-                opt = transport_solve_small(m, nc, ldc, cost, flow, supply, deficit, lane);
+                opt = transport_solve_small(m, nc, ldc, cost, flow, cmask, supply, deficit, lane);
             }
             if (lane == 0) {
                 double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;

@@ -111,6 +111,7 @@ struct wmd_engine {
     DevBuf ap[32];
     unsigned long long *stats = nullptr;        // device [6]
     bool profiling = false;
+    int slot_mask = 1;                           // 0 (WMD_SERIAL=1): every chunk on one stream, for clean per-kernel timings
     std::vector<ProfRec> prof;
     double prof_ms[WMD_K_COUNT] = { 0 };
     int64_t prof_n[WMD_K_COUNT] = { 0 };
@@ -277,6 +278,12 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
             FastArgs F;
             F.vc = vc; F.plan = E->plan; F.R = R; F.S = E->fast_S; F.ldr = E->fast_ldr; F.rowbytes = E->ld * 4;
             F.negzero2 = 0x8000000080000000ull;
+            F.common_iters = 1; F._pad = 0;
+            if (E->fast_PL > 1) {
+                int cm = 1 << 30;
+                for (int o = 0; o < E->fast_PL; ++o) cm = std::min(cm, E->plan.len[o] >> 3);
+                F.common_iters = std::max(cm, 1);
+            }
             F.stages = P.stages; F.nstages = P.nstages;
             F.tiles = tiles; F.tile_stride = tile_stride; F.maxc = maxc;
             const int grid = (int)std::min<int64_t>(Bc, (int64_t)E->sm_count);
@@ -461,7 +468,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
     const int64_t CH = chunk_pairs(ml1, ml2);
     int slot = 0;
-    for (int64_t c0 = 0; c0 < J.npairs; c0 += CH, slot ^= 1) {
+    for (int64_t c0 = 0; c0 < J.npairs; c0 += CH, slot = (slot ^ 1) & E->slot_mask) {
         const int32_t Bc = (int32_t)std::min<int64_t>(CH, J.npairs - c0);
         Workspace &W = E->ws[slot];
         cudaStream_t st = E->streams[slot];
@@ -526,7 +533,7 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_join[0], 0));        // stats reset precedes both streams' kernels
     const int64_t CH = chunk_pairs(ml1, ml2);
     int slot = 0;
-    for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot ^= 1) {
+    for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot = (slot ^ 1) & E->slot_mask) {
         const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - c0);
         Workspace &W = E->ws[slot];
         if (!status) { if ((rc = W.status.ensure((size_t)Bc * 4))) return rc; }
@@ -822,6 +829,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if (const char *v = getenv("WMD_COST_CHUNK_ITERS")) max_iters = std::max(1, std::min(16, atoi(v)));
         if ((rc = build_cost_chunks(E, max_iters))) return bail(rc);
         if ((rc = setup_fast_path(E))) return bail(rc);
+        if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
     if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));

@@ -77,7 +77,7 @@ int main()
     A.plan.nops = 4;
     const int st[4] = { 0, 72, 144, 216 }, ln[4] = { 72, 72, 72, 84 }, ad[4] = { 0, 1, 0, 2 };
     for (int i = 0; i < 4; ++i) { A.plan.start[i] = st[i]; A.plan.len[i] = ln[i]; A.plan.adds[i] = ad[i]; }
-    A.R = 40; A.S = 1; A.rowbytes = ld * 4; A.negzero2 = 0x8000000080000000ull;
+    A.R = 40; A.S = 1; A.common_iters = 9; A.rowbytes = ld * 4; A.negzero2 = 0x8000000080000000ull;
     A.tiles = tiles; A.tile_stride = 512; A.maxc = maxc;
     cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     const int reps = 200;
