@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--vocab", type=int, default=10_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs"],
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs", "latency"],
                     help="pairs = BASELINE configs[1] (the driver's headline); allpairs = configs[3], top-k with RWMD pruning")
     ap.add_argument("--docs", type=int, default=100_000, help="allpairs: documents in the set (self join)")
     ap.add_argument("--topk", type=int, default=16)
@@ -454,10 +454,56 @@ def run_allpairs(a):
         dist.destroy_process_group()
 
 
+def run_latency(a):
+    """BASELINE configs[2]: the in-loop caller's shape -- one collate batch per call (src/loader.py:60: 256 Yelp
+    pairs or 128 book pairs of noised sentences) through the host entry, pageable numpy buffers, wall clock per
+    call incl. H2D / D2H.  Reports the median and p99 latency and the resulting pairs/s, next to the oracle port
+    of the reference loop on one core (the reference's collate runs single-threaded in the main process)."""
+    import torch
+    from consistent__style_transfer_b200.engine import WMDEngine
+    from oracle import wmd_oracle
+    table = workload.make_table(a.vocab, 100, seed=0)              # d = 100: the reference's real embedding width
+    eng = WMDEngine(table, device=0)
+    out = {}
+    for shape, B in (("yelp", 256), ("book", 128)):
+        ids1, off1, ids2, off2 = workload.make_pairs(B * 64, shape, "noised", V=a.vocab, seed=5, batch=B)
+        calls = []
+        for b in range(64):
+            lo, hi = b * B, (b + 1) * B
+            calls.append((ids1[off1[lo]:off1[hi]].copy(), (off1[lo:hi + 1] - off1[lo]).copy(),
+                          ids2[off2[lo]:off2[hi]].copy(), (off2[lo:hi + 1] - off2[lo]).copy()))
+        for c in calls[:8]:
+            eng.wmd_pairs(*c)
+        lat = []
+        for rep in range(4):
+            for c in calls:
+                t0 = time.perf_counter()
+                eng.wmd_pairs(*c)
+                lat.append(time.perf_counter() - t0)
+        lat = np.array(lat)
+        # reference-shaped loop on ONE core for the same batch
+        words = ["w%06d" % i for i in range(a.vocab)]
+        kv = wmd_oracle.KeyedVectorsOracle(words, table)
+        c = calls[0]
+        t0 = time.perf_counter()
+        for p in range(B):
+            kv.wmdistance([words[t] for t in c[0][c[1][p]:c[1][p + 1]]], [words[t] for t in c[2][c[3][p]:c[3][p + 1]]])
+        cpu_s = time.perf_counter() - t0
+        out[f"{shape}_batch{B}"] = {"median_us": float(np.median(lat) * 1e6), "p99_us": float(np.quantile(lat, 0.99) * 1e6),
+                                    "pairs_per_s": float(B / np.median(lat)), "cpu_reference_port_1core_ms": cpu_s * 1e3,
+                                    "speedup_vs_1core": float(cpu_s / np.median(lat))}
+    print(json.dumps({"metric": "wmd_batch_latency", "unit": "us", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "one pretrain collate batch per call (noised pairs, d=100, V=%d), host entry, pageable buffers" % a.vocab},
+                      "batches": out}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "latency":
+        run_latency(args)
     elif args.mode == "allpairs":
         run_allpairs(args)
     else:

@@ -111,6 +111,8 @@ struct wmd_engine {
     DevBuf ap[32];
     unsigned long long *stats = nullptr;        // device [6]
     bool profiling = false;
+    int solve_blocks_per_sm = 8;                 // K3 grid cap per SM (WMD_SOLVE_BLOCKS): fewer leaves room for a co-resident K2b
+    int fast_stage_cap = kFastMaxStages;         // K2b ring depth cap (WMD_FAST_S)
     int slot_mask = 1;                           // 0 (WMD_SERIAL=1): every chunk on one stream, for clean per-kernel timings
     std::vector<ProfRec> prof;
     double prof_ms[WMD_K_COUNT] = { 0 };
@@ -199,10 +201,12 @@ int setup_fast_path(wmd_engine *E)
     const int ldr = ldr4 * 4;
     const size_t pitch = (size_t)ldr * 4;
     int R = (int)std::min<size_t>(kStageRowsMax, (48 * 1024) / pitch);
+    if (const char *v = getenv("WMD_FAST_R")) R = std::max(8, std::min(R, atoi(v)));
     if (R < 8) return WMD_OK;                                 // very wide embeddings: general kernel only
     const size_t stage_bytes = (size_t)kStageDescBytes + (size_t)R * pitch;
     const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 1024;    // static barriers / counters
     int S = (int)std::min<size_t>(kFastMaxStages, budget / stage_bytes);
+    if (const char *v = getenv("WMD_FAST_S")) S = std::max(2, std::min(S, atoi(v)));
     if (S < 2) return WMD_OK;
     const SumPlan &pl = E->plan;
     int PL = 1;
@@ -389,7 +393,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
                                        : solve_smem_per_warp(S.mr, S.mc, S.ldc, S.use_global);
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
-        int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (cls == kClsC ? 2 : 8));
+        int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (cls == kClsC ? 2 : E->solve_blocks_per_sm));
         grid = std::max(grid, 1);
         S.scratch = nullptr;
         if (S.use_global) {
@@ -830,6 +834,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if ((rc = build_cost_chunks(E, max_iters))) return bail(rc);
         if ((rc = setup_fast_path(E))) return bail(rc);
         if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
+        if (const char *v = getenv("WMD_SOLVE_BLOCKS")) E->solve_blocks_per_sm = std::max(1, atoi(v));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
     if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));
