@@ -279,6 +279,14 @@ def run_b200(a):
     prof = eng.profile(reset=True)
     eng.set_profiling(False)
     stats = eng.last_stats()
+    # one more profiled pass with the chunks serialised on a single stream: the kernels' own durations
+    eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
+    for _ in range(2):
+        flush.fill_(1)
+        dev_step()
+    barrier()
+    prof_serial = eng.profile(reset=True)
+    eng.set_profiling(False); eng.set_serial(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -339,6 +347,11 @@ def run_b200(a):
                 "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in kern.items()},
                 "launches_per_step": {k: v["launches"] // a.steps for k, v in kern.items()},
                 "per_kernel_achieved_gbs": {k: alg_bytes_step / (v["ms"] / a.steps / 1e3) / 1e9 for k, v in kern.items()},
+                "standalone": {"note": "same step with all chunks on one stream (2 extra untimed-for-the-headline steps): "
+                                       "the dominant kernel's own launch durations",
+                               "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in prof_serial.items() if v["launches"] > 0},
+                               "achieved": alg_bytes_step / (prof_serial[dom]["ms"] / 2 / 1e3) / 1e9,
+                               "frac": alg_bytes_step / (prof_serial[dom]["ms"] / 2 / 1e3) / 1e9 / peak},
                 "whole_step_achieved": alg_bytes_step / (total_ms / a.steps / 1e3) / 1e9}
     launches = sum(v["launches"] for v in kern.values())
 

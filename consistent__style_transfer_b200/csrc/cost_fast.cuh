@@ -207,7 +207,7 @@ __device__ __forceinline__ void leaf_2x4(const float *const (&a)[2], const float
             }
     }
     e += 8;
-#pragma unroll 2
+#pragma unroll 4
     for (int it = 1; it < common; ++it, e += 8) {                 // uniform trip count: the warp stays in lockstep
         Q4 x[2], y[4];
 #pragma unroll

@@ -1073,6 +1073,13 @@ int wmd_set_profiling(wmd_handle E, int32_t enabled)
     return WMD_OK;
 }
 
+int wmd_set_serial(wmd_handle E, int32_t enabled)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    E->slot_mask = enabled ? 0 : 1;
+    return WMD_OK;
+}
+
 int wmd_get_profile(wmd_handle E, double *ms, int64_t *launches, int32_t reset)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");

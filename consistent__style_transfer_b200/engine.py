@@ -239,6 +239,10 @@ class WMDEngine:
     def set_profiling(self, enabled: bool):
         _lib.check(self._L.wmd_set_profiling(self._handle(), int(bool(enabled))))
 
+    def set_serial(self, enabled: bool):
+        """One internal stream instead of two: per-kernel event times without co-scheduling effects."""
+        _lib.check(self._L.wmd_set_serial(self._handle(), int(bool(enabled))))
+
     def profile(self, reset: bool = True):
         ms = (ctypes.c_double * len(KERNEL_KINDS))()
         n = (ctypes.c_int64 * len(KERNEL_KINDS))()

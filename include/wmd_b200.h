@@ -148,6 +148,9 @@ int wmd_allpairs_topk_host(wmd_handle h, const int32_t *idsA, const int64_t *off
 
 /* When enabled, every kernel launch is bracketed by CUDA events on its own stream. */
 int wmd_set_profiling(wmd_handle h, int32_t enabled);
+/* When enabled, all chunks of a call run on ONE internal stream (no overlap between the solver of one
+ * chunk and the cost kernels of the next): slower, but the per-kernel event times are the kernels' own. */
+int wmd_set_serial(wmd_handle h, int32_t enabled);
 #define WMD_K_NBOW   0
 #define WMD_K_COST   1
 #define WMD_K_SOLVE  2

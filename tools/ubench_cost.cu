@@ -67,7 +67,9 @@ int main()
     std::vector<uint4> descs;
     make_descs(descs, 9, 9, 0, 0);
     make_descs(descs, 10, 9, 18, 1);
-    const int ntiles = (int)descs.size(), nrows = 37;
+    make_descs(descs, 8, 8, 37, 2);
+    make_descs(descs, 9, 10, 53, 3);
+    const int ntiles = (int)descs.size(), nrows = 72;
     uint4 *ddesc; cudaMalloc(&ddesc, descs.size() * 16); cudaMemcpy(ddesc, descs.data(), descs.size() * 16, cudaMemcpyHostToDevice);
     float *tiles; cudaMalloc(&tiles, 1 << 20);
     unsigned *maxc; cudaMalloc(&maxc, 4096); cudaMemset(maxc, 0, 4096);
@@ -79,17 +81,17 @@ int main()
     for (int i = 0; i < 4; ++i) { A.plan.start[i] = st[i]; A.plan.len[i] = ln[i]; A.plan.adds[i] = ad[i]; }
     A.R = 40; A.S = 1; A.common_iters = 9; A.rowbytes = ld * 4; A.negzero2 = 0x8000000080000000ull;
     A.tiles = tiles; A.tile_stride = 512; A.maxc = maxc;
-    cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
     const int reps = 200;
     printf("stage: %d tiles, %d rows\n", ntiles, nrows);
-    for (int ldr : { 300, 304, 308, 312, 316, 320 })
-        for (int warps : { 4, 8, 12, 16 }) {
+    for (int ldr : { 300 })
+        for (int warps : { 1, 2, 4, 8, 12, 16 }) {
             A.ldr = ldr;
-            bench_kernel<<<148, warps * 32, 100 * 1024>>>(A, ddesc, ntiles, nrows, dtab, reps, cyc);
+            bench_kernel<<<148, warps * 32, 120 * 1024>>>(A, ddesc, ntiles, nrows, dtab, reps, cyc);
             cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
             long long c[148]; cudaMemcpy(c, cyc, sizeof c, cudaMemcpyDeviceToHost);
             long long mx = 0; for (int i = 0; i < 148; ++i) mx = c[i] > mx ? c[i] : mx;
-            printf("ldr %3d warps %2d: %.1f SM-cycles per tile task (%s)\n", ldr, warps, (double)mx / ((double)reps * ntiles), cudaGetErrorString(e));
+            printf("ldr %3d warps %2d: %.1f SM-cycles per tile task, %.0f cycles per batch per warp (%s)\n", ldr, warps, (double)mx / ((double)reps * ntiles), (double)mx / ((double)reps * ((ntiles + 4 * warps - 1) / (4 * warps))), cudaGetErrorString(e));
         }
     return 0;
 }
