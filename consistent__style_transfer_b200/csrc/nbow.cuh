@@ -22,6 +22,9 @@ struct PairWork {
     int32_t *meta;                    // per pair: class | swap flag
     double *pqn, *extra;              // per pair: PQn, maxSum - minSum
     unsigned long long *stats;        // [6]: tokens, uniques, cells, solved pairs, max rows, max cols
+    double *wt1, *wt2;                // WMD_MODE_EXACT: nBOW weights count/len per token slot (else unused)
+    int32_t exact;                    // != 0: no cancellation / quantisation, weights out, every pair class A
+    int32_t _pad;
 };
 
 // Unique in-vocabulary rows of one document, sorted by key. All lanes return (u, nvalid).
@@ -132,6 +135,15 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
         for (int i = lane; i < u1; i += kWarp) { w1[i] = __ddiv_rn((double)scnt1[i], dn1); part1[i] = -1; }
         for (int j = lane; j < u2; j += kWarp) { w2[j] = __ddiv_rn((double)scnt2[j], dn2); part2[j] = -1; }
         __syncwarp();
+        if (w.exact) {                                                   // WMD_MODE_EXACT: rows, counts and weights only
+            for (int i = lane; i < u1; i += kWarp) { w.rows1[o1 + i] = srow1[i]; w.cnt1[o1 + i] = scnt1[i]; w.wt1[o1 + i] = w1[i]; }
+            for (int j = lane; j < u2; j += kWarp) { w.rows2[o2 + j] = srow2[j]; w.cnt2[o2 + j] = scnt2[j]; w.wt2[o2 + j] = w2[j]; }
+            if (lane == 0) { w.u12[q] = u1 | (u2 << 16); w.meta[q] = kClsA; w.pqn[q] = 1.0; w.extra[q] = 0.0; status[p] = 0; }
+            st_unq += u1 + u2; st_cells += (unsigned long long)u1 * u2; st_solved += 1;
+            st_mr = max(st_mr, u1); st_mc = max(st_mc, u2);
+            __syncwarp();
+            continue;
+        }
         for (int i = lane; i < u1; i += kWarp) {
             const int r = srow1[i];
             for (int j = 0; j < u2; ++j)

@@ -471,4 +471,198 @@ emd_solve_kernel(const __grid_constant__ SolveArgs A)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// WMD_MODE_EXACT: the real-valued transportation optimum in FP64 -- no 1e6 grid, no cancellation
+// (an additive mode: the reference's pyemd never computes it).  Rows = the unique
+// tokens of doc1 with the nBOW weights count/len as supplies, columns = doc2's; costs are the float32
+// distances widened to double.  Same primal-dual method as transport_solve<KC> on doubles; masses
+// below kExactTol are treated as shipped (the two weight vectors sum to 1 only up to rounding).
+// One warp per pair; cost / flow matrices in L2-resident global scratch, duals and tree in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr double kExactTol = 1e-13;
+
+__device__ __forceinline__ double warp_min_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(kFull, v, o); v = w < v ? w : v; }
+    return v;
+}
+
+struct ExactArgs {
+    DocSide s1, s2;
+    int64_t p0;
+    int32_t npairs;
+    int32_t mr, mc;                   // capacity of the per-warp arrays: rows, columns
+    int32_t ldc;
+    const int32_t *u12;
+    const double *wt1, *wt2;          // nBOW weights at the pairs' work slots (K1, exact flag)
+    const float *tiles;
+    int64_t tile_stride;
+    const float *maxc;
+    double *scratch;                  // [warps, 2 * mr * ldc]
+    unsigned int *counter;
+    double *out;
+    int32_t *status;
+};
+
+__host__ __device__ inline size_t exact_smem_per_warp(int mr, int mc) { return (size_t)mr * (8 + 8 + 8 + 4) + (size_t)mc * 4 + 8; }
+
+template <int KC>
+__device__ double transport_solve_f64(int m, int nc, int ldc, const double *cost, double *flow, double *su, double *srowdist,
+                                      int *srowpred, const double *ssupply, int *sway, double (&deficit)[KC], int lane)
+{
+    const double kBig = 1e300;
+    double v[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) v[k] = 0.0;
+    for (int i = lane; i < m; i += kWarp) su[i] = 0.0;
+    for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0.0;
+    __syncwarp();
+    for (int r = 0; r < m; ++r) {
+        double sup = ssupply[r];
+        while (sup > kExactTol) {
+            double minv[KC]; int way[KC];
+            unsigned used = 0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { minv[k] = kBig; way[k] = -1; }
+            for (int i = lane; i < m; i += kWarp) srowdist[i] = (i == r) ? 0.0 : -1.0;
+            __syncwarp();
+            {
+                const double ur = su[r];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int c = lane + 32 * k;
+                    if (c < nc) { minv[k] = cost[r * ldc + c] - ur - v[k]; way[k] = r; }
+                }
+            }
+            double D = 0.0, def = 0.0; int j0 = 0;
+            for (;;) {
+                double best = kBig; int bk = 0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (!((used >> k) & 1u) && minv[k] < best) { best = minv[k]; bk = k; }
+                const double delta = warp_min_f64(best);
+                if (!(delta < kBig)) return -1.0;                // every column used: the remaining supply is rounding noise
+                const int jl = __ffs(__ballot_sync(kFull, best == delta)) - 1;
+                const int jk = __shfl_sync(kFull, bk, jl);
+                double mydef = 0.0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) if (k == jk) mydef = deficit[k];
+                def = __shfl_sync(kFull, mydef, jl);
+                if (lane == jl) used |= 1u << jk;
+                j0 = jl + 32 * jk;
+                D = delta;
+                if (def > kExactTol) break;
+                for (int base = 0; base < m; base += kWarp) {    // rows shipping into the saturated column join the tree
+                    const int i = base + lane;
+                    bool isnew = false;
+                    if (i < m && srowdist[i] < 0.0 && flow[i * ldc + j0] > kExactTol) { isnew = true; srowdist[i] = delta; srowpred[i] = j0; }
+                    unsigned mask = __ballot_sync(kFull, isnew);
+                    while (mask) {
+                        const int row = base + __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const double ui = su[row];
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            if (c < nc && !((used >> k) & 1u)) {
+                                const double cand = delta + cost[row * ldc + c] - ui - v[k];
+                                if (cand < minv[k]) { minv[k] = cand; way[k] = row; }
+                            }
+                        }
+                    }
+                }
+            }
+            for (int i = lane; i < m; i += kWarp) { const double dd = srowdist[i]; if (dd >= 0.0) su[i] += D - dd; }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if ((used >> k) & 1u) v[k] -= D - minv[k];
+                const int c = lane + 32 * k;
+                if (c < nc) sway[c] = way[k];
+            }
+            __syncwarp();
+            double amt = sup < def ? sup : def;
+            for (int j = j0;;) {
+                const int i = sway[j];
+                if (i == r) break;
+                const int jp = srowpred[i];
+                const double f = flow[i * ldc + jp];
+                amt = f < amt ? f : amt;
+                j = jp;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int j = j0;;) {
+                    const int i = sway[j];
+                    flow[i * ldc + j] += amt;
+                    if (i == r) break;
+                    const int jp = srowpred[i];
+                    flow[i * ldc + jp] -= amt;
+                    j = jp;
+                }
+            }
+            sup -= amt;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) if (lane + 32 * k == j0) deficit[k] -= amt;
+            __syncwarp();
+            if (!(amt > 0.0)) break;                             // a zero-flow tree arc: nothing more to ship from this row
+        }
+    }
+    double tot = 0.0;
+    for (int x = lane; x < m * ldc; x += kWarp) {
+        const int c = x % ldc;
+        if (c < nc) tot += flow[x] * cost[x];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFull, tot, o);
+    return tot;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(128)
+emd_solve_exact_kernel(const __grid_constant__ ExactArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_x[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char *sb = smem_x + (size_t)wib * ((exact_smem_per_warp(A.mr, A.mc) + 15) & ~(size_t)15);
+    double *su = reinterpret_cast<double *>(sb), *srowdist = su + A.mr, *ssupply = srowdist + A.mr;
+    int *srowpred = reinterpret_cast<int *>(ssupply + A.mr), *sway = srowpred + A.mr;
+    double *cost = A.scratch + ((size_t)blockIdx.x * wpb + wib) * 2 * (size_t)A.mr * A.ldc;
+    double *flow = cost + (size_t)A.mr * A.ldc;
+    int64_t tok1, tok2;
+    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = (int)atomicAdd(A.counter, 8u);
+        q0 = __shfl_sync(kFull, q0, 0);
+        if (q0 >= A.npairs) break;
+        const int q1 = min(A.npairs, q0 + 8);
+        for (int q = q0; q < q1; ++q) {
+            const int uu = A.u12[q];
+            const int u1 = uu & 0xffff, u2 = uu >> 16;
+            if (u1 == 0 || u2 == 0) continue;                    // early-out already written by K1
+            const int64_t p = A.p0 + q;
+            const float maxc_f = A.maxc[q];
+            if (!(maxc_f > 0.f)) {                               // S4: all-zero distance matrix
+                if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+                continue;
+            }
+            int64_t a1, a2; int l;
+            doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
+            const double *w1 = A.wt1 + slot_off(A.s1, tok1, q, a1), *w2 = A.wt2 + slot_off(A.s2, tok2, q, a2);
+            for (int i = lane; i < u1; i += kWarp) ssupply[i] = w1[i];
+            double deficit[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { const int c = lane + 32 * k; deficit[k] = c < u2 ? w2[c] : 0.0; }
+            const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+            for (int x = lane; x < u1 * u2; x += kWarp) { const int i = x / u2, j = x - i * u2; cost[i * A.ldc + j] = (double)tile[x]; }
+            __syncwarp();
+            const double opt = transport_solve_f64<KC>(u1, u2, A.ldc, cost, flow, su, srowdist, srowpred, ssupply, sway, deficit, lane);
+            if (lane == 0) A.out[p] = opt < 0.0 ? __longlong_as_double(0x7ff8000000000000LL) : opt;
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace wmd

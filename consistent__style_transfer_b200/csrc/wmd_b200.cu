@@ -70,13 +70,13 @@ struct Workspace {
     DevBuf ids1, ids2, off1, off2;              // staged inputs (host entries)
     DevBuf rows1, cnt1, ip1, rows2, cnt2, ip2;  // per token slot
     DevBuf u12, meta, pqn, extra, maxc;         // per pair
-    DevBuf tiles, out, status, scratch, plan;
+    DevBuf tiles, out, status, scratch, plan, wt1, wt2;
     DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
     DevBuf counters;                            // 4 x unsigned
     void release()
     {
         DevBuf *all[] = { &ids1, &ids2, &off1, &off2, &rows1, &cnt1, &ip1, &rows2, &cnt2, &ip2, &u12, &meta, &pqn,
-                          &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &lb, &l1, &l2, &am1, &am2, &counters };
+                          &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &wt1, &wt2, &lb, &l1, &l2, &am1, &am2, &counters };
         for (DevBuf *b : all) b->release();
     }
 };
@@ -250,6 +250,7 @@ struct ChunkOut {
     double *lb = nullptr, *l1 = nullptr, *l2 = nullptr;
     int32_t *am1 = nullptr, *am2 = nullptr; // chunk-relative token offsets
     bool solve = true;
+    int mode = WMD_MODE_PYEMD;
 };
 
 // K2: cost tiles of pairs [p0, p0 + Bc): the planned fast path for pairs that fit a stage, the
@@ -344,6 +345,11 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
     pw.rows2 = W.rows2.as<int32_t>(); pw.cnt2 = W.cnt2.as<int32_t>(); pw.ip2 = W.ip2.as<int32_t>();
     pw.u12 = W.u12.as<int32_t>(); pw.meta = W.meta.as<int32_t>(); pw.pqn = W.pqn.as<double>(); pw.extra = W.extra.as<double>();
     pw.stats = E->stats;
+    pw.exact = O.mode == WMD_MODE_EXACT; pw._pad = 0; pw.wt1 = nullptr; pw.wt2 = nullptr;
+    if (pw.exact) {
+        if ((rc = W.wt1.ensure((size_t)tokcap1 * 8)) || (rc = W.wt2.ensure((size_t)tokcap2 * 8))) return rc;
+        pw.wt1 = W.wt1.as<double>(); pw.wt2 = W.wt2.as<double>();
+    }
     const Vocab vc = make_vocab(E);
     {
         const int Lp = ML;
@@ -375,6 +381,27 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
     }
     if (!O.solve) return WMD_OK;
     // ---- K3 (work counters were zeroed before K2)
+    if (O.mode == WMD_MODE_EXACT) {
+        ExactArgs X;
+        X.s1 = s1; X.s2 = s2; X.p0 = p0; X.npairs = Bc;
+        X.mr = ml1; X.mc = ml2; X.ldc = ml2 | 1;
+        X.u12 = pw.u12; X.wt1 = pw.wt1; X.wt2 = pw.wt2;
+        X.tiles = W.tiles.as<float>(); X.tile_stride = tile_stride; X.maxc = W.maxc.as<float>();
+        X.counter = W.counters.as<unsigned int>() + kClsA;
+        X.out = O.out; X.status = O.status;
+        const int wpb = 4;
+        const size_t per_warp = (exact_smem_per_warp(X.mr, X.mc) + 15) & ~(size_t)15;
+        const size_t smem = per_warp * wpb;
+        const int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (ML > 64 ? 1 : 4));
+        if ((rc = W.scratch.ensure((size_t)grid * wpb * 2 * X.mr * X.ldc * 8))) return rc;
+        X.scratch = W.scratch.as<double>();
+        Prof pr(E, WMD_K_SOLVE, st);
+        if (ml2 <= 32) emd_solve_exact_kernel<1><<<grid, wpb * 32, smem, st>>>(X);
+        else if (ml2 <= 64) emd_solve_exact_kernel<2><<<grid, wpb * 32, smem, st>>>(X);
+        else emd_solve_exact_kernel<8><<<grid, wpb * 32, smem, st>>>(X);
+        CK(cudaGetLastError());
+        return WMD_OK;
+    }
     for (int cls = kClsA; cls <= kClsC; ++cls) {
         if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
         if (cls == kClsC && ML < 64) continue;
@@ -454,6 +481,7 @@ struct HostJob {
     const int32_t *ids1; const int64_t *off1; const int32_t *ids2; const int64_t *off2; int64_t npairs;
     double *out; int32_t *status;
     bool rwmd = false, solve = true;
+    int mode = WMD_MODE_PYEMD;
     double *lb = nullptr, *l1 = nullptr, *l2 = nullptr; int32_t *am1 = nullptr, *am2 = nullptr;
 };
 
@@ -489,7 +517,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
         s1.ids = W.ids1.as<int32_t>() - J.off1[c0]; s1.off = W.off1.as<int64_t>();
         s2.ids = W.ids2.as<int32_t>() - J.off2[c0]; s2.off = W.off2.as<int64_t>();
         ChunkOut O;
-        O.out = W.out.as<double>(); O.status = W.status.as<int32_t>(); O.solve = J.solve; O.rwmd = J.rwmd;
+        O.out = W.out.as<double>(); O.status = W.status.as<int32_t>(); O.solve = J.solve; O.rwmd = J.rwmd; O.mode = J.mode;
         if (J.rwmd) {
             if ((rc = W.lb.ensure((size_t)Bc * 8)) || (rc = W.l1.ensure((size_t)Bc * 8)) || (rc = W.l2.ensure((size_t)Bc * 8)) ||
                 (rc = W.am1.ensure((size_t)std::max<int64_t>(t1, 1) * 4)) || (rc = W.am2.ensure((size_t)std::max<int64_t>(t2, 1) * 4)))
@@ -520,7 +548,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
 
 // shared body of the device entries: fork from the caller's stream, chunk, join back; no host sync
 int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t total1, int64_t total2,
-                int32_t ml1, int32_t ml2, int64_t npairs, double *out, int32_t *status, cudaStream_t us)
+                int32_t ml1, int32_t ml2, int64_t npairs, double *out, int32_t *status, cudaStream_t us, int mode = WMD_MODE_PYEMD)
 {
     int rc;
     if ((rc = set_device(E))) return rc;
@@ -542,7 +570,7 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
         Workspace &W = E->ws[slot];
         if (!status) { if ((rc = W.status.ensure((size_t)Bc * 4))) return rc; }
         ChunkOut O;
-        O.out = out; O.status = status;
+        O.out = out; O.status = status; O.mode = mode;
         int64_t p0 = c0;
         DocSide a = s1, b = s2;
         if (!status) {
@@ -929,9 +957,10 @@ int wmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, const
                    int64_t npairs, int32_t mode, double *out, int32_t *status)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
     if (!out && npairs > 0) return fail(WMD_EINVAL, "out is null");
     HostJob J{ ids1, off1, ids2, off2, npairs, out, status };
+    J.mode = mode;
     return run_host_job(E, J);
 }
 
@@ -951,24 +980,24 @@ int wmd_pairs_dev(wmd_handle E, const int32_t *ids1, const int64_t *off1, int64_
                   int64_t npairs, int32_t mode, double *out, int32_t *status, void *stream)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
     if (npairs > 0 && (!off1 || !off2)) return fail(WMD_EINVAL, "null offsets");
     DocSide s1{}, s2{};
     s1.ids = ids1; s1.off = off1; s2.ids = ids2; s2.off = off2;
-    return run_dev_job(E, s1, s2, total1, total2, max_len1, max_len2, npairs, out, status, (cudaStream_t)stream);
+    return run_dev_job(E, s1, s2, total1, total2, max_len1, max_len2, npairs, out, status, (cudaStream_t)stream, mode);
 }
 
 int wmd_pairs_padded_dev(wmd_handle E, const int32_t *a, int32_t L1, const int32_t *b, int32_t L2, int64_t npairs,
                          int32_t pad_id, int32_t mode, double *out, int32_t *status, void *stream)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
     if (npairs > 0 && (!a || !b)) return fail(WMD_EINVAL, "null ids");
     if (L1 <= 0 || L2 <= 0) return fail(WMD_EINVAL, "padded lengths must be positive");
     DocSide s1{}, s2{};
     s1.ids = a; s1.off = nullptr; s1.L = L1; s1.pad_id = pad_id; s1.has_pad = 1;
     s2.ids = b; s2.off = nullptr; s2.L = L2; s2.pad_id = pad_id; s2.has_pad = 1;
-    return run_dev_job(E, s1, s2, npairs * L1, npairs * L2, L1, L2, npairs, out, status, (cudaStream_t)stream);
+    return run_dev_job(E, s1, s2, npairs * L1, npairs * L2, L1, L2, npairs, out, status, (cudaStream_t)stream, mode);
 }
 
 int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t ndocs,

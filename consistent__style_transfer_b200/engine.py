@@ -15,7 +15,9 @@ from . import _lib
 from ._lib import c_f32p, c_f64p, c_i32p, c_i64p
 
 KERNEL_KINDS = ("nbow", "cost", "solve", "rwmd", "misc")
-MODE_PYEMD = 0
+MODE_PYEMD = 0      # the reference's value: pyemd's 1e6-grid integer optimum (bit-faithful)
+MODE_EXACT = 1      # additive: the real-valued transportation optimum in FP64
+_MODES = {"pyemd": MODE_PYEMD, "exact": MODE_EXACT, MODE_PYEMD: MODE_PYEMD, MODE_EXACT: MODE_EXACT}
 
 
 def _np(a, dtype):
@@ -95,8 +97,9 @@ class WMDEngine:
 
     # -- scoring: host buffers --------------------------------------------------------------
     def wmd_pairs(self, ids1, off1, ids2, off2, out: Optional[np.ndarray] = None,
-                  status: Optional[np.ndarray] = None):
-        """WMD of CSR-packed pairs held in host memory. Returns (float64[B], int32 status[B])."""
+                  status: Optional[np.ndarray] = None, mode="pyemd"):
+        """WMD of CSR-packed pairs held in host memory. Returns (float64[B], int32 status[B]).
+        mode "pyemd" (default) is the reference's value; "exact" the un-quantised FP64 optimum."""
         ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
         off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
         B = off1.shape[0] - 1
@@ -107,7 +110,7 @@ class WMDEngine:
         if status is None:
             status = np.empty(B, np.int32)
         _lib.check(self._L.wmd_pairs_host(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p),
-                                          _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B, MODE_PYEMD,
+                                          _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B, _MODES[mode],
                                           _ptr(out, c_f64p), _ptr(status, c_i32p)))
         return out, status
 
@@ -182,7 +185,7 @@ class WMDEngine:
         return idx, dist, info
 
     # -- scoring: device tensors (torch) ----------------------------------------------------
-    def wmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, out=None, status=None):
+    def wmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, out=None, status=None, mode="pyemd"):
         """CSR pairs in torch CUDA tensors (int32 ids, int64 offsets) -> float64 CUDA tensor.
         Stream-ordered on torch's current stream; no host synchronisation."""
         import torch
@@ -197,7 +200,7 @@ class WMDEngine:
         stream = torch.cuda.current_stream(ids1.device).cuda_stream
         _lib.check(self._L.wmd_pairs_dev(self._handle(), ids1.data_ptr(), off1.data_ptr(), ids1.numel(), int(max_len1),
                                          ids2.data_ptr(), off2.data_ptr(), ids2.numel(), int(max_len2),
-                                         B, MODE_PYEMD, out.data_ptr(), status.data_ptr(), stream))
+                                         B, _MODES[mode], out.data_ptr(), status.data_ptr(), stream))
         return out, status
 
     def wmd_pairs_padded(self, a, b, pad_id: int = 0, out=None, status=None):

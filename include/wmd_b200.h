@@ -64,6 +64,8 @@ typedef struct wmd_engine *wmd_handle;
 
 /* distance definition */
 #define WMD_MODE_PYEMD 0   /* pyemd emd_hat_gd_metric: 1e6-grid integer optimum (bit-faithful to the reference) */
+#define WMD_MODE_EXACT 1   /* additive: the real-valued transportation optimum in FP64 (no grid, no cancellation);
+                              differs from the reference's value by ~1e-6 relative */
 
 /* lifetime ------------------------------------------------------------------------------------ */
 

@@ -316,3 +316,34 @@ def allpairs_topk_bruteforce(table: np.ndarray, idsA, offA, idsB, offB, k: int,
         idx[i] = order; dist[i] = d[order]
     assert lenB.shape[0] == nB
     return idx, dist
+
+
+# --------------------------------------------------------------------------- #
+# WMD_MODE_EXACT (additive, not the reference's value): the real-valued optimum by an LP solver.
+# --------------------------------------------------------------------------- #
+def wmd_exact_lp(table: np.ndarray, doc1_rows: Sequence[int], doc2_rows: Sequence[int],
+                 rank: Optional[np.ndarray] = None) -> float:
+    """Transportation LP between the two nBOW histograms with float32 distances widened to float64,
+    solved by scipy's HiGHS.  Same early-outs as the quantised path (inf / 0.0)."""
+    from scipy.optimize import linprog
+    r1, _, w1 = nbow(doc1_rows, rank)
+    r2, _, w2 = nbow(doc2_rows, rank)
+    if len(r1) == 0 or len(r2) == 0:
+        return float("inf")
+    if len(r1) == 1 and len(r2) == 1 and r1[0] == r2[0]:
+        return 0.0
+    D = np.empty((len(r1), len(r2)), np.float64)
+    for i, a in enumerate(r1):
+        for j, b in enumerate(r2):
+            D[i, j] = float(dist_f32(table[a], table[b]))
+    if D.max() == 0.0:
+        return float("inf")
+    m, n = D.shape
+    A_eq = np.zeros((m + n, m * n))
+    for i in range(m):
+        A_eq[i, i * n:(i + 1) * n] = 1.0
+    for j in range(n):
+        A_eq[m + j, j::n] = 1.0
+    res = linprog(D.ravel(), A_eq=A_eq[:-1], b_eq=np.concatenate([w1, w2])[:-1], bounds=(0, None), method="highs")
+    assert res.status == 0, res.message
+    return float(res.fun)

@@ -193,3 +193,25 @@ def test_symmetry_and_permutation_invariance_full_size(eng_mod):
     v0, s0 = e.wmd_pairs(ids1, off1, ids1, off1)
     assert np.all(v0 == 0.0) and set(np.unique(s0)) <= {0, 2}
     e.close()
+
+
+@pytest.mark.parametrize("shape,B,d", [("yelp", 300, 300), ("book", 120, 100), ("fixed:40", 40, 64)])
+def test_exact_mode_matches_lp(eng_mod, oracle, shape, B, d):
+    """WMD_MODE_EXACT (additive): the un-quantised FP64 optimum against scipy HiGHS on the same nBOW
+    histograms and float32 distances, 1e-9 relative; statuses as in the default mode; and within the
+    1e-5 that the reference's 1e6 grid can move a value."""
+    V = 800
+    table = workload.make_table(V, d, seed=3)
+    ids1, off1, ids2, off2 = workload.make_pairs(B, shape, "noised" if shape == "yelp" else "independent", V=V, seed=21)
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2, mode="exact")
+    ref, rst = e.wmd_pairs(ids1, off1, ids2, off2)                       # pyemd mode
+    assert np.array_equal(st, rst)
+    for p in range(B):
+        want = oracle.wmd_exact_lp(table, ids1[off1[p]:off1[p + 1]], ids2[off2[p]:off2[p + 1]])
+        if math.isinf(want) or want == 0.0:
+            assert got[p] == want
+        else:
+            assert abs(got[p] - want) <= 1e-9 * max(1.0, want), (p, got[p], want)
+            assert abs(got[p] - ref[p]) <= 2e-5 * max(1.0, want)
+    e.close()

@@ -112,3 +112,22 @@ def test_symmetry_permutation_and_bounds(oracle):
     for p in range(0, 200, 7):
         r = oracle.rwmd_pair(table, ids1[off1[p]:off1[p + 1]], ids2[off2[p]:off2[p + 1]])
         assert r[0] <= v12[p] * (1 + 1e-5) + 1e-9
+
+
+def test_exact_lp_oracle_close_to_quantised(oracle):
+    """The additive exact mode's checker (HiGHS LP) against the quantised reference value: they differ
+    only by what the 1e6 grid can move (median 1e-6, max ~1e-5 relative)."""
+    import numpy as np
+    from consistent__style_transfer_b200 import workload
+    V = 300
+    table = workload.make_table(V, 50, seed=8)
+    ids1, off1, ids2, off2 = workload.make_pairs(60, "yelp", "independent", V=V, seed=2)
+    q, st = oracle.batch_wmd(table, ids1, off1, ids2, off2)
+    worst = 0.0
+    for p in range(60):
+        lp = oracle.wmd_exact_lp(table, ids1[off1[p]:off1[p + 1]], ids2[off2[p]:off2[p + 1]])
+        if np.isfinite(q[p]) and q[p] > 0:
+            worst = max(worst, abs(lp - q[p]) / q[p])
+        else:
+            assert lp == q[p]
+    assert 0.0 < worst < 3e-5
