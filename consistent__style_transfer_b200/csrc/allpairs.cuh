@@ -130,7 +130,9 @@ lb_tile_kernel(const __grid_constant__ LbArgs A)
 {
     __shared__ double l2t[32][33];
     const int x = threadIdx.x, y = threadIdx.y;
-    const int jb = blockIdx.x * 32, ib = blockIdx.y * 32;
+    // query blocks vary fastest: the 32-column slice of Z_B (V x 128 B = 1.3 MB) of one corpus block stays
+    // L2-hot across all query blocks that reuse it
+    const int ib = blockIdx.x * 32, jb = blockIdx.y * 32;
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
     // L2(i, j): lanes along i (Z_A rows are contiguous in i), y = j
     {

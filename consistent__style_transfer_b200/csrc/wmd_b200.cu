@@ -792,7 +792,7 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             L.nvalB = B[AP_NVALB].as<int32_t>(); L.nB = (int32_t)nB;
             L.ZB = B[AP_ZB].as<float>(); L.ldzb = ldzb; L.ZA = B[AP_ZA].as<float>(); L.ldza = ldza;
             L.LB = B[AP_LB].as<float>(); L.ldlb = ldlb;
-            dim3 g2((unsigned)((nB + 31) / 32), (unsigned)((ni + 31) / 32));
+            dim3 g2((unsigned)((ni + 31) / 32), (unsigned)((nB + 31) / 32));
             lb_tile_kernel<<<g2, dim3(32, 32), 0, st>>>(L);
             CK(cudaGetLastError());
             st_local[0] += (int64_t)ni * nB;
