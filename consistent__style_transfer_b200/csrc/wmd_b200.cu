@@ -201,11 +201,15 @@ int setup_fast_path(wmd_engine *E)
     if ((ldr4 & 1) == 0) ldr4++;
     const int ldr = ldr4 * 4;
     const size_t pitch = (size_t)ldr * 4;
+    const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 1024;    // static barriers / counters
     int R = (int)std::min<size_t>(kStageRowsMax, (48 * 1024) / pitch);
+    // wide embeddings: prefer stages that still hold a 20 + 20 token pair (or as close as three stages allow)
+    // over a deeper ring -- pairs that do not fit a stage fall to the much slower general kernel
+    if (R < 40 && budget / 3 > (size_t)kStageDescBytes + pitch)
+        R = std::max(R, (int)std::min<size_t>(40, (budget / 3 - kStageDescBytes) / pitch));
     if (const char *v = getenv("WMD_FAST_R")) R = std::max(8, std::min(R, atoi(v)));
     if (R < 8) return WMD_OK;                                 // very wide embeddings: general kernel only
     const size_t stage_bytes = (size_t)kStageDescBytes + (size_t)R * pitch;
-    const size_t budget = std::min<size_t>(E->smem_optin, 227 * 1024) - 1024;    // static barriers / counters
     int S = (int)std::min<size_t>(kFastMaxStages, budget / stage_bytes);
     if (const char *v = getenv("WMD_FAST_S")) S = std::max(2, std::min(S, atoi(v)));
     if (S < 2) return WMD_OK;
@@ -215,6 +219,14 @@ int setup_fast_path(wmd_engine *E)
     for (int o = 0; o < pl.nops; ++o) minlen = minlen && pl.len[o] >= 8;
     if (minlen && pl.nops == 4 && pl.adds[0] == 0 && pl.adds[1] == 1 && pl.adds[2] == 0 && pl.adds[3] == 2) PL = 4;
     else if (minlen && pl.nops == 2 && pl.adds[0] == 0 && pl.adds[1] == 1) PL = 2;
+    // lanes of one tile work on PL leaves at once: if the leaves start a multiple of 32 floats apart (d = 256, 512, ...)
+    // all of them hit the same banks on every load -- walk the leaves one after the other instead
+    if (PL > 1) {
+        bool collide = false;
+        for (int o = 1; o < PL; ++o) collide = collide || ((pl.start[o] - pl.start[0]) % 32 == 0);
+        if (collide) PL = 1;
+    }
+    if (const char *v = getenv("WMD_FAST_PL")) { const int f = atoi(v); if (f == 1 || (f == 2 && PL >= 2) || (f == 4 && PL == 4)) PL = f; }
     const size_t smem = (size_t)S * stage_bytes;
     cudaError_t e;
     if (PL == 4) e = cudaFuncSetAttribute(cost_tiles_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

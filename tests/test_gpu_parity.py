@@ -63,6 +63,10 @@ def test_nbow_bit_exact(eng_mod, oracle, use_rank):
     (100, "yelp", "noised", 4000), (300, "yelp", "independent", 4000), (300, "yelp", "noised", 2000),
     (100, "book", "noised", 1500), (300, "book", "independent", 1000), (7, "yelp", "independent", 500),
     (130, "yelp", "independent", 500),
+    # widths whose numpy leaves start 32 floats apart (bank-aligned: the cost kernel walks the leaves one after the other),
+    # a width with 8 leaves, and one that needs the two-leaf variant
+    (256, "yelp", "independent", 800), (512, "yelp", "independent", 800), (1000, "yelp", "noised", 300),
+    (200, "book", "independent", 400),
 ])
 def test_wmd_pairs_match_oracle(eng_mod, oracle, d, shape, variant, B):
     V = 2000
