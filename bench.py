@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--vocab", type=int, default=10_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs", "latency"],
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs", "latency", "sweep"],
                     help="pairs = BASELINE configs[1] (the driver's headline); allpairs = configs[3], top-k with RWMD pruning")
     ap.add_argument("--docs", type=int, default=100_000, help="allpairs: documents in the set (self join)")
     ap.add_argument("--topk", type=int, default=16)
@@ -511,10 +511,55 @@ def run_latency(a):
     eng.close()
 
 
+def run_sweep(a):
+    """BASELINE configs[4]: fixed document lengths 8 -> 256 (both sides, independent draws, d=300), 2^18 pairs each
+    (2^14 from 128 tokens up), device-resident inputs, CUDA-event timed; per-kernel times from a serialised pass."""
+    import torch
+    from consistent__style_transfer_b200.engine import WMDEngine
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    table = workload.make_table(a.vocab, a.d, seed=0)
+    eng = WMDEngine(table, device=0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = {}
+    for L in (8, 16, 32, 64, 128, 256):
+        n = 1 << (18 if L < 128 else 14)
+        ids1, off1, ids2, off2 = workload.make_pairs(n, f"fixed:{L}", "independent", V=a.vocab, seed=L)
+        d = [torch.from_numpy(x).to(dev) for x in (ids1, off1, ids2, off2)]
+        out = torch.empty(n, dtype=torch.float64, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(max(3, a.steps)):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        stats = eng.last_stats()
+        eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
+        eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
+        torch.cuda.synchronize()
+        prof = eng.profile(reset=True)
+        eng.set_profiling(False); eng.set_serial(False)
+        t = statistics.median(ms)
+        alg = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * n
+        rows[str(L)] = {"pairs": n, "ms": t, "pairs_per_s": n / (t / 1e3), "mean_unique_tokens_per_side": stats["uniques"] / (2 * n),
+                        "algorithmic_gb_per_s": alg / (t / 1e3) / 1e9,
+                        "kernel_ms_serial": {k: v["ms"] for k, v in prof.items() if v["launches"] > 0}}
+    print(json.dumps({"metric": "wmd_length_sweep_pairs_per_sec", "unit": "pairs/s", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"fixed lengths 8..256 both sides, independent, d={a.d}, V={a.vocab}",
+                                 "l2": "256 MiB flush write between timed steps"}, "lengths": rows}), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sweep":
+        run_sweep(args)
     elif args.mode == "latency":
         run_latency(args)
     elif args.mode == "allpairs":

@@ -60,7 +60,47 @@ struct PlanArgs {
     unsigned int *nstages;             // zeroed by the host
 };
 
-// One warp per block of 32 consecutive pairs (lane = pair).
+// Rows and tile descriptors of one unit: the ni x nj block at (i0, j0) of pair q's u1 x u2 tile.
+// r1 / r2 point at the block's first table row on each side.
+__device__ __forceinline__ void emit_unit(StageRec &S, int rowbase, int tilebase, int q, const int32_t *r1, const int32_t *r2,
+                                          int ni, int nj, int i0, int j0, int u2)
+{
+    for (int k = 0; k < ni; ++k) S.rows[rowbase + k] = r1[k];
+    for (int k = 0; k < nj; ++k) S.rows[rowbase + ni + k] = r2[k];
+    const int tr = pick_orientation(ni, nj);
+    const int na = tr ? nj : ni, nb = tr ? ni : nj;
+    const int abase = rowbase + (tr ? ni : 0), bbase = rowbase + (tr ? 0 : ni);
+    const int TI = (na + 1) >> 1, TJ = (nb + 3) >> 2;
+    const unsigned sr = tr ? (unsigned)TI : (unsigned)(TI * u2);
+    const unsigned sc = tr ? (unsigned)(TJ * u2) : (unsigned)TJ;
+    const int tiles = TI * TJ;
+    for (int t = 0; t < tiles; ++t) {
+        const int ti = t / TJ, tj = t - ti * TJ;
+        const int va = (ti + TI < na) ? 2 : 1;
+        int vb = 1;
+#pragma unroll
+        for (int c = 1; c < 4; ++c) vb += (tj + c * TJ < nb);
+        unsigned rowsA[2], rowsB[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) rowsA[r] = (unsigned)(abase + (r < va ? ti + r * TI : ti));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rowsB[c] = (unsigned)(bbase + (c < vb ? tj + c * TJ : tj));
+        const unsigned off = tr ? (unsigned)((i0 + tj) * u2 + j0 + ti) : (unsigned)((i0 + ti) * u2 + j0 + tj);
+        uint4 w;
+        w.x = rowsA[0] | (rowsA[1] << 8) | (rowsB[0] << 16) | (rowsB[1] << 24);
+        w.y = rowsB[2] | (rowsB[3] << 8) | ((unsigned)va << 16) | ((unsigned)vb << 24);
+        w.z = sr | (sc << 16);
+        w.w = (unsigned)q | (off << 16);
+        *reinterpret_cast<uint4 *>(&S.tiles[tilebase + t]) = w;
+    }
+}
+
+// Side length of the blocks a pair that does not fit one stage is cut into (every block is a stage of its own)
+__host__ __device__ inline int split_block_max(int R) { return R / 2 < 20 ? R / 2 : 20; }
+
+// One warp per block of 32 consecutive pairs (lane = pair).  Pairs that fit a stage are packed greedily with
+// their neighbours; longer ones are cut into blocks of at most split_block_max(R) rows per side, one stage
+// each (a table row is then fetched once per block it takes part in).
 __global__ void __launch_bounds__(128)
 cost_plan_kernel(const __grid_constant__ PlanArgs A)
 {
@@ -68,20 +108,27 @@ cost_plan_kernel(const __grid_constant__ PlanArgs A)
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    const int bmax = split_block_max(A.R);
     for (int blk = gw; blk * 32 < A.npairs; blk += nw) {
         const int q = blk * 32 + lane;
         int u1 = 0, u2 = 0;
         if (q < A.npairs) { const int u = A.u12[q]; u1 = u & 0xffff; u2 = u >> 16; }
-        if (!fast_fits(u1, u2, A.R, A.T)) { u1 = 0; u2 = 0; }
-        const int tr = pick_orientation(u1, u2);
-        const int rows = u1 + u2;
-        const int tiles = u1 > 0 ? unit_tiles(u1, u2, tr) : 0;
-        int rs = rows, ts = tiles;
+        if (u1 == 0 || u2 == 0) { u1 = 0; u2 = 0; }
+        const bool big = u1 > 0 && !fast_fits(u1, u2, A.R, A.T);
+        // geometry of a split pair
+        const int nbi = big ? (u1 + bmax - 1) / bmax : 0, nbj = big ? (u2 + bmax - 1) / bmax : 0;
+        const int BI = big ? (u1 + nbi - 1) / nbi : 0, BJ = big ? (u2 + nbj - 1) / nbj : 0;
+        const int nblk = nbi * nbj;
+        const int pu1 = big ? 0 : u1, pu2 = big ? 0 : u2;             // what takes part in the greedy packing
+        const int rows = pu1 + pu2;
+        const int tiles = pu1 > 0 ? unit_tiles(pu1, pu2, pick_orientation(pu1, pu2)) : 0;
+        int rs = rows, ts = tiles, bs = nblk;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int r = __shfl_up_sync(kFull, rs, o), t2 = __shfl_up_sync(kFull, ts, o);
-            if (lane >= o) { rs += r; ts += t2; }
+            const int r = __shfl_up_sync(kFull, rs, o), t2 = __shfl_up_sync(kFull, ts, o), b2 = __shfl_up_sync(kFull, bs, o);
+            if (lane >= o) { rs += r; ts += t2; bs += b2; }
         }
+        const int total_big = __shfl_sync(kFull, bs, 31);
         // greedy packing of consecutive pairs into stages (stage numbers are reserved once per warp:
         // one same-address atomic per stage serialises in L2 and cost 40 us per launch)
         int my_stage = -1, my_rowbase = 0, my_tilebase = 0;
@@ -103,44 +150,51 @@ cost_plan_kernel(const __grid_constant__ PlanArgs A)
             base_r += tot_r; base_t += tot_t; start = end;
         }
         int sbase = 0;
-        if (lane == 0 && nlocal) sbase = (int)atomicAdd(A.nstages, (unsigned)nlocal);
+        if (lane == 0 && nlocal + total_big) sbase = (int)atomicAdd(A.nstages, (unsigned)(nlocal + total_big));
         sbase = __shfl_sync(kFull, sbase, 0);
         if (my_stage >= 0) my_stage += sbase;
         if (hdr_r > 0) { A.stages[my_stage].nrows = hdr_r; A.stages[my_stage].ntiles = hdr_t; }
-        // every pair writes its own rows and tile descriptors
-        if (my_stage >= 0 && rows > 0) {
-            StageRec &S = A.stages[my_stage];
-            int64_t a1, a2; int l;
-            doc_span(A.s1, A.p0 + q, a1, l); doc_span(A.s2, A.p0 + q, a2, l);
-            const int32_t *r1 = A.rows1 + slot_off(A.s1, tok1, q, a1), *r2 = A.rows2 + slot_off(A.s2, tok2, q, a2);
-            for (int k = 0; k < u1; ++k) S.rows[my_rowbase + k] = r1[k];
-            for (int k = 0; k < u2; ++k) S.rows[my_rowbase + u1 + k] = r2[k];
-            const int na = tr ? u2 : u1, nb = tr ? u1 : u2;
-            const int abase = my_rowbase + (tr ? u1 : 0), bbase = my_rowbase + (tr ? 0 : u1);
-            const int TI = (na + 1) >> 1, TJ = (nb + 3) >> 2;
-            const unsigned sr = tr ? (unsigned)TI : (unsigned)(TI * u2);
-            const unsigned sc = tr ? (unsigned)(TJ * u2) : (unsigned)TJ;
-            for (int t = 0; t < tiles; ++t) {
-                const int ti = t / TJ, tj = t - ti * TJ;
-                const int va = (ti + TI < na) ? 2 : 1;
-                int vb = 1;
-#pragma unroll
-                for (int c = 1; c < 4; ++c) vb += (tj + c * TJ < nb);
-                unsigned rowsA[2], rowsB[4];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) rowsA[r] = (unsigned)(abase + (r < va ? ti + r * TI : ti));
-#pragma unroll
-                for (int c = 0; c < 4; ++c) rowsB[c] = (unsigned)(bbase + (c < vb ? tj + c * TJ : tj));
-                const unsigned off = tr ? (unsigned)(tj * u2 + ti) : (unsigned)(ti * u2 + tj);
-                uint4 w;
-                w.x = rowsA[0] | (rowsA[1] << 8) | (rowsB[0] << 16) | (rowsB[1] << 24);
-                w.y = rowsB[2] | (rowsB[3] << 8) | ((unsigned)va << 16) | ((unsigned)vb << 24);
-                w.z = sr | (sc << 16);
-                w.w = (unsigned)q | (off << 16);
-                *reinterpret_cast<uint4 *>(&S.tiles[my_tilebase + t]) = w;
+        int64_t a1 = 0, a2 = 0;
+        if (u1 > 0) { int l; doc_span(A.s1, A.p0 + q, a1, l); doc_span(A.s2, A.p0 + q, a2, l); }
+        const int64_t o1 = u1 > 0 ? slot_off(A.s1, tok1, q, a1) : 0, o2 = u1 > 0 ? slot_off(A.s2, tok2, q, a2) : 0;
+        // every packed pair writes its own rows and tile descriptors
+        if (my_stage >= 0 && rows > 0)
+            emit_unit(A.stages[my_stage], my_rowbase, my_tilebase, q, A.rows1 + o1, A.rows2 + o2, u1, u2, 0, 0, u2);
+        // split pairs: the warp emits the blocks of one pair together, a block (= a stage) per lane
+        unsigned bigmask = __ballot_sync(kFull, big);
+        while (bigmask) {
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const int bq = __shfl_sync(kFull, q, src), bu1 = __shfl_sync(kFull, u1, src), bu2 = __shfl_sync(kFull, u2, src);
+            const int bnbj = __shfl_sync(kFull, nbj, src), bBI = __shfl_sync(kFull, BI, src), bBJ = __shfl_sync(kFull, BJ, src);
+            const int bn = __shfl_sync(kFull, nblk, src);
+            const int first = sbase + nlocal + __shfl_sync(kFull, bs - nblk, src);
+            const long long bo1 = __shfl_sync(kFull, (long long)o1, src), bo2 = __shfl_sync(kFull, (long long)o2, src);
+            for (int b = lane; b < bn; b += kWarp) {
+                const int bi = b / bnbj, bj = b - bi * bnbj;
+                const int i0 = bi * bBI, j0 = bj * bBJ;
+                const int ni = min(bBI, bu1 - i0), nj = min(bBJ, bu2 - j0);
+                StageRec &S = A.stages[first + b];
+                S.nrows = ni + nj;
+                S.ntiles = unit_tiles(ni, nj, pick_orientation(ni, nj));
+                emit_unit(S, 0, 0, bq, A.rows1 + bo1 + i0, A.rows2 + bo2 + j0, ni, nj, i0, j0, bu2);
             }
         }
     }
+}
+
+// Upper bound of the stages cost_plan_kernel can emit for Bc pairs with at most ml1 x ml2 unique rows and tok1 / tok2
+// token slots in total: sum over pairs of ceil(u1 / b) * ceil(u2 / b) <= ml2 * tok1 / b^2 + (tok1 + tok2) / b + Bc.
+inline int64_t plan_stage_bound(int64_t Bc, int ml1, int ml2, int64_t tok1, int64_t tok2, int R, int T)
+{
+    // nothing is split when even the largest possible pair fits a stage (rows AND tile tasks, as fast_fits)
+    const int a = ml1 < ml2 ? ml1 : ml2, c = ml1 < ml2 ? ml2 : ml1;
+    const int t0 = ((a + 1) / 2) * ((c + 3) / 4), t1 = ((c + 1) / 2) * ((a + 3) / 4);
+    if (ml1 + ml2 <= R && (t0 < t1 ? t1 : t0) <= T) return Bc;
+    const int64_t b = split_block_max(R) > 0 ? split_block_max(R) : 1;
+    tok1 = tok1 < Bc * (int64_t)ml1 ? tok1 : Bc * (int64_t)ml1;
+    tok2 = tok2 < Bc * (int64_t)ml2 ? tok2 : Bc * (int64_t)ml2;
+    return (int64_t)ml2 * tok1 / (b * b) + (tok1 + tok2) / b + 2 * Bc + 64;
 }
 
 struct FastArgs {

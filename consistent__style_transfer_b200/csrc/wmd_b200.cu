@@ -270,8 +270,8 @@ struct ChunkOut {
 // general kernel for the rest.  rows1 / rows2 / u12 come from K1 (or are synthesised by the
 // distance-table build); tiles is [Bc, tile_stride]; maxc receives the per-pair maximum (float bits).
 int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2, int64_t p0, int32_t Bc,
-                int32_t ml1, int32_t ml2, const int32_t *rows1, const int32_t *rows2, const int32_t *u12,
-                float *tiles, int64_t tile_stride, unsigned int *maxc)
+                int32_t ml1, int32_t ml2, int64_t tokcap1, int64_t tokcap2, const int32_t *rows1, const int32_t *rows2,
+                const int32_t *u12, float *tiles, int64_t tile_stride, unsigned int *maxc)
 {
     int rc;
     const Vocab vc = make_vocab(E);
@@ -282,7 +282,7 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
         const int R = E->fast_R, T = kStageTilesMax;
         bool need_general = true;
         if (R > 0) {
-            if ((rc = W.plan.ensure((size_t)Bc * sizeof(StageRec)))) return rc;
+            if ((rc = W.plan.ensure((size_t)plan_stage_bound(Bc, ml1, ml2, tokcap1, tokcap2, R, T) * sizeof(StageRec)))) return rc;
             PlanArgs P;
             P.s1 = s1; P.s2 = s2; P.p0 = p0; P.npairs = Bc; P.R = R; P.T = T; P._pad = 0;
             P.rows1 = rows1; P.rows2 = rows2; P.u12 = u12;
@@ -310,10 +310,7 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
             else if (E->fast_PL == 2) cost_tiles_fast_kernel<2><<<grid, kFastThreads, E->fast_smem, st>>>(F);
             else cost_tiles_fast_kernel<1><<<grid, kFastThreads, E->fast_smem, st>>>(F);
             CK(cudaGetLastError());
-            // every pair of this chunk fits a stage when the longest possible one does
-            const int a = std::min(ml1, ml2), b = std::max(ml1, ml2);
-            const int worst_tiles = std::min(((a + 1) / 2) * ((b + 3) / 4), ((b + 1) / 2) * ((a + 3) / 4));
-            need_general = ml1 + ml2 > R || worst_tiles > T;
+            need_general = false;                         // longer pairs are cut into blocks by the plan
         }
         if (need_general) {
             CostArgs A;
@@ -375,7 +372,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         CK(cudaGetLastError());
     }
     // ---- K2
-    if ((rc = launch_cost(E, W, st, s1, s2, p0, Bc, ml1, ml2, pw.rows1, pw.rows2, pw.u12, W.tiles.as<float>(), tile_stride,
+    if ((rc = launch_cost(E, W, st, s1, s2, p0, Bc, ml1, ml2, tokcap1, tokcap2, pw.rows1, pw.rows2, pw.u12, W.tiles.as<float>(), tile_stride,
                           W.maxc.as<unsigned int>())))
         return rc;
     // ---- K5 (optional)
@@ -661,7 +658,7 @@ int ensure_dtab(wmd_engine *E, cudaStream_t st)
         dtab_make_pairs_kernel<<<(Bc + 255) / 256, 256, 0, st>>>((int32_t)V, BS, nb, q0, Bc, W.rows1.as<int32_t>(), W.rows2.as<int32_t>(),
                                                                  W.u12.as<int32_t>(), E->ap[AP_BIJ].as<int32_t>());
         if (cudaGetLastError() != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "dtab_make_pairs_kernel launch failed"); }
-        if ((rc = launch_cost(E, W, st, s1, s2, 0, Bc, BS, BS, W.rows1.as<int32_t>(), W.rows2.as<int32_t>(), W.u12.as<int32_t>(),
+        if ((rc = launch_cost(E, W, st, s1, s2, 0, Bc, BS, BS, (int64_t)Bc * BS, (int64_t)Bc * BS, W.rows1.as<int32_t>(), W.rows2.as<int32_t>(), W.u12.as<int32_t>(),
                               W.tiles.as<float>(), tile_stride, W.maxc.as<unsigned int>()))) { cudaFree(D); return rc; }
         dtab_scatter_kernel<<<Bc, 128, 0, st>>>((int32_t)V, BS, Bc, W.u12.as<int32_t>(), E->ap[AP_BIJ].as<int32_t>(), W.tiles.as<float>(),
                                                 tile_stride, D);
