@@ -7,11 +7,10 @@
 // threshold node), and the un-normalisation  dist = opt / PQn / Cn + (maxSum - minSum) * maxC.
 //
 // pyemd runs successive shortest paths over adjacency lists; that shape is wrong for a warp.
-// Here the residual problem (m supplying rows x nc columns) lives in shared memory as dense
-// int32 cost and flow matrices and the warp runs a primal-dual (Hungarian-style) method:
-// rows are admitted one at a time, each Dijkstra runs over the dense bipartite residual graph
-// with one column (or KC columns) per lane -- relax a row = one shared-memory read per lane,
-// pick the next column = one REDUX.MIN + one ballot.  All quantities are integers below 2^31,
+// Here the residual problem (m supplying rows x nc columns) is a dense int32 cost matrix and the
+// warp runs a primal-dual (Hungarian-style) method: rows are admitted one at a time, each Dijkstra
+// runs over the dense bipartite residual graph with one column (or KC columns) per lane -- relax a
+// row = one read per lane and column word, pick the next column = one REDUX.MIN + one ballot.  All quantities are integers below 2^31,
 // so the optimum is exact and equals the reference's regardless of the pivot path.
 #pragma once
 #include "common.cuh"
@@ -29,8 +28,8 @@ struct SolveArgs {
     int32_t cls;                      // class this launch serves (kClsA also finalises kClsNone pairs with status 0)
     int32_t mr, mc;                   // row / column capacity of the per-warp matrices
     int32_t ldc;                      // column pitch (odd)
-    int32_t use_global;               // matrices in global scratch (class C)
-    int32_t *scratch;                 // [warps, 2 * mr * ldc] when use_global
+    int32_t use_global;               // cost matrix in global scratch as well (class C)
+    int32_t *scratch;                 // classes B / C: [warps, mr * ldc] flow (+ the same again for cost when use_global)
     const int32_t *ip1, *ip2;
     const int32_t *u12, *meta;
     const double *pqn, *extra;
@@ -41,130 +40,6 @@ struct SolveArgs {
     double *out;
     int32_t *status;
 };
-
-__host__ __device__ inline size_t solve_smem_per_warp(int mr, int mc, int ldc, bool use_global)
-{
-    size_t ints = (size_t)mr * 4 /* u, rowdist, rowpred, supply */ + (size_t)mr /* ridx */ + 2 * (size_t)mc /* cidx, way */;
-    if (!use_global) ints += 2 * (size_t)mr * ldc;
-    return ints * 4;
-}
-
-template <int KC>
-__device__ __forceinline__ void relax_row(const int *cost, int ldc, int nc, int row, int di, int ui, int lane,
-                                          const int (&v)[KC], unsigned used, int (&minv)[KC], int (&way)[KC])
-{
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int c = lane + 32 * k;
-        if (c < nc && !((used >> k) & 1u)) {
-            const int cand = di + cost[row * ldc + c] - ui - v[k];
-            if (cand < minv[k]) { minv[k] = cand; way[k] = row; }
-        }
-    }
-}
-
-// Exact min-cost of shipping supply[] (rows) into deficit[] (columns; sum equal). Returns sum f*c.
-template <int KC>
-__device__ long long transport_solve(int m, int nc, int ldc, const int *cost, int *flow,
-                                     int *su, int *srowdist, int *srowpred, const int *ssupply, int *sway,
-                                     int (&deficit)[KC], int lane)
-{
-    int v[KC];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) v[k] = 0;
-    for (int i = lane; i < m; i += kWarp) su[i] = 0;
-    for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0;
-    __syncwarp();
-
-    for (int r = 0; r < m; ++r) {
-        int sup = ssupply[r];
-        while (sup > 0) {
-            int minv[KC], way[KC];
-            unsigned used = 0;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) { minv[k] = kIntInf; way[k] = -1; }
-            for (int i = lane; i < m; i += kWarp) srowdist[i] = (i == r) ? 0 : -1;
-            __syncwarp();
-            relax_row<KC>(cost, ldc, nc, r, 0, su[r], lane, v, used, minv, way);
-            int D, j0, def;
-            for (;;) {
-                int best = kIntInf, bk = 0;
-#pragma unroll
-                for (int k = 0; k < KC; ++k)
-                    if (!((used >> k) & 1u) && minv[k] < best) { best = minv[k]; bk = k; }
-                const int delta = __reduce_min_sync(kFull, best);
-                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
-                const int jl = __ffs(__ballot_sync(kFull, best == delta)) - 1;
-                const int jk = __shfl_sync(kFull, bk, jl);
-                int mydef = 0;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) if (k == jk) mydef = deficit[k];
-                def = __shfl_sync(kFull, mydef, jl);
-                if (lane == jl) used |= 1u << jk;
-                j0 = jl + 32 * jk;
-                D = delta;
-                if (def > 0) break;
-                // column j0 is saturated: every row shipping into it joins the tree at distance delta
-                for (int base = 0; base < m; base += kWarp) {
-                    const int i = base + lane;
-                    bool isnew = false;
-                    if (i < m && srowdist[i] < 0 && flow[i * ldc + j0] > 0) {
-                        isnew = true; srowdist[i] = delta; srowpred[i] = j0;
-                    }
-                    unsigned mask = __ballot_sync(kFull, isnew);
-                    while (mask) {
-                        const int b = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        relax_row<KC>(cost, ldc, nc, base + b, delta, su[base + b], lane, v, used, minv, way);
-                    }
-                }
-            }
-            // dual update: tree nodes move by (D - their distance); others keep their potentials
-            for (int i = lane; i < m; i += kWarp) {
-                const int dd = srowdist[i];
-                if (dd >= 0) su[i] += D - dd;
-            }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if ((used >> k) & 1u) v[k] -= D - minv[k];
-                const int c = lane + 32 * k;
-                if (c < nc) sway[c] = way[k];
-            }
-            __syncwarp();
-            // augment along the tree path j0 -> ... -> r
-            int amt = min(sup, def);
-            for (int j = j0;;) {
-                const int i = sway[j];
-                if (i == r) break;
-                const int jp = srowpred[i];
-                amt = min(amt, flow[i * ldc + jp]);
-                j = jp;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                for (int j = j0;;) {
-                    const int i = sway[j];
-                    flow[i * ldc + j] += amt;
-                    if (i == r) break;
-                    const int jp = srowpred[i];
-                    flow[i * ldc + jp] -= amt;
-                    j = jp;
-                }
-            }
-            sup -= amt;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) if (lane + 32 * k == j0) deficit[k] -= amt;
-            __syncwarp();
-        }
-    }
-    long long tot = 0;
-    for (int x = lane; x < m * ldc; x += kWarp) {
-        const int c = x % ldc;
-        if (c < nc) tot += (long long)flow[x] * (long long)cost[x];
-    }
-    return warp_sum_ll(tot);
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // Class A (m <= 32 rows, nc <= 32 columns incl. the dummy): the same primal-dual method with the
@@ -364,114 +239,294 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
     }
 }
 
-template <int KC>
-__global__ void __launch_bounds__(256)
-emd_solve_kernel(const __grid_constant__ SolveArgs A)
+// ------------------------------------------------------------------------------------------------
+// Classes B (<= 64 x 64) and C (<= 256 x 257): the class-A design with KR row words and KC column
+// words.  Lane L is rows L + 32k (k < KR) and columns L + 32k (k < KC); duals, tentative distances and
+// tree predecessors stay in registers, the tree / used-column sets are KR / KC warp-uniform words,
+// and cmask[j][KR] (shared memory) says which rows ship into column j.  The flow matrix is only ever
+// touched along augmenting paths and where cmask has a bit, so it lives in global scratch and is never
+// cleared (a cell is written, not added to, when its bit is off).  Costs: shared memory (class B) or
+// L2-resident global scratch (class C).  The previous version kept dense cost AND flow per warp in
+// shared memory (35 kB: 4 warps per SM) and found the rows of a saturated column by scanning a flow
+// column with dependent loads; profiles/README.md has the before / after.
+// ------------------------------------------------------------------------------------------------
+template <int KR, int KC>
+__host__ __device__ inline size_t solve_multi_smem_per_warp(int mr, int mc, int ldc, bool cost_global)
+{
+    size_t ints = (size_t)mr + mc + (size_t)mc * KR;
+    if (!cost_global) ints += (size_t)mr * ldc;
+    return ((ints + 3) & ~(size_t)3) * 4;
+}
+
+template <int K>
+__device__ __forceinline__ int sel_word(const int (&a)[K], int k)
+{
+    int x = a[0];
+#pragma unroll
+    for (int t = 1; t < K; ++t) if (t == k) x = a[t];
+    return x;
+}
+
+template <int KR, int KC>
+__device__ long long transport_solve_multi(int m, int nc, int ldc, const int *cost, int *flow, unsigned *cmask,
+                                           const int (&supply)[KR], int (&deficit)[KC], int lane)
+{
+    int u[KR], rdist[KR], rpred[KR];
+    int v[KC], minv[KC], way[KC];
+    unsigned tree[KR], used[KC], inval[KC];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) u[k] = 0;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        v[k] = 0;
+        const int lo = 32 * k;                                   // columns >= nc do not exist: permanently "used"
+        inval[k] = nc >= lo + 32 ? 0u : (nc <= lo ? kFull : (kFull << (nc - lo)));
+    }
+    for (int x = lane; x < nc * KR; x += kWarp) cmask[x] = 0;
+    __syncwarp();
+    const unsigned lbit = 1u << lane;
+
+    for (int r = 0; r < m; ++r) {
+        const int rk = r >> 5, rl = r & 31;
+        int sup = __shfl_sync(kFull, sel_word<KR>(supply, rk), rl);
+        while (sup > 0) {
+#pragma unroll
+            for (int k = 0; k < KR; ++k) { tree[k] = k == rk ? (1u << rl) : 0u; rdist[k] = 0; rpred[k] = -1; }
+            {
+                const int ur = __shfl_sync(kFull, sel_word<KR>(u, rk), rl);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    used[k] = inval[k];
+                    way[k] = r;
+                    minv[k] = (inval[k] & lbit) ? kIntInf : cost[r * ldc + lane + 32 * k] - ur - v[k];
+                }
+            }
+            int delta, j0, jl, jk, def;
+            for (;;) {
+                int best = kIntInf, bk = 0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int key = (used[k] & lbit) ? kIntInf : minv[k];
+                    if (key < best) { best = key; bk = k; }
+                }
+                delta = __reduce_min_sync(kFull, best);
+                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
+                jl = __ffs(__ballot_sync(kFull, best == delta)) - 1;
+                jk = __shfl_sync(kFull, bk, jl);
+                j0 = jl + 32 * jk;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) if (k == jk) used[k] |= 1u << jl;
+                def = __shfl_sync(kFull, sel_word<KC>(deficit, jk), jl);
+                if (def > 0) {
+                    // direct arc out of the root row: ship and keep searching (see transport_solve_small)
+                    if (__shfl_sync(kFull, sel_word<KC>(way, jk), jl) != r) break;
+                    const int amt = min(sup, def);
+                    if (lane == jl) {
+                        const unsigned w = cmask[j0 * KR + rk];
+                        int *f = flow + r * ldc + j0;
+                        *f = (w >> rl) & 1u ? *f + amt : amt;
+                        cmask[j0 * KR + rk] = w | (1u << rl);
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
+                    }
+                    __syncwarp();
+                    sup -= amt;
+                    def -= amt;
+                    if (sup == 0) break;
+                }
+                // rows shipping into the saturated column join the tree at distance delta
+#pragma unroll
+                for (int w = 0; w < KR; ++w) {
+                    unsigned nr = cmask[j0 * KR + w] & ~tree[w];
+                    tree[w] |= nr;
+                    if (nr & lbit) { rdist[w] = delta; rpred[w] = j0; }
+                    while (nr) {
+                        const int b = __ffs(nr) - 1;
+                        nr &= nr - 1;
+                        const int i = 32 * w + b;
+                        const int base = delta - __shfl_sync(kFull, u[w], b);
+                        const int *crow = cost + i * ldc + lane;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            if (!(used[k] & lbit)) {
+                                const int cand = base + crow[32 * k] - v[k];
+                                if (cand < minv[k]) { minv[k] = cand; way[k] = i; }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KR; ++k) if (tree[k] & lbit) u[k] += delta - rdist[k];     // dual update (tree nodes only)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) if (used[k] & ~inval[k] & lbit) v[k] -= delta - minv[k];
+            if (sup == 0) break;                                 // the row emptied on a direct arc
+            // tree path j0 -> ... -> r in pieces of 32 hops (hop h = row pi starts shipping into column pj and
+            // stops shipping amt into its tree predecessor column pjp); pass 0 finds the bottleneck, the
+            // push follows at once when the path fits one piece, otherwise pass 1 walks it again
+            int amt = min(sup, def);
+            for (int pass = 0; pass < 2; ++pass) {
+                int j = j0;
+                bool done = false, single = true;
+                while (!done) {
+                    int pi = 0, pj = 0, pjp = -1, nh = 0;
+                    for (; nh < kWarp;) {
+                        const int i = __shfl_sync(kFull, sel_word<KC>(way, j >> 5), j & 31);
+                        const int jp = __shfl_sync(kFull, sel_word<KR>(rpred, i >> 5), i & 31);
+                        if (lane == nh) { pi = i; pj = j; pjp = i == r ? -1 : jp; }
+                        ++nh;
+                        if (i == r) { done = true; break; }
+                        j = jp;
+                    }
+                    if (!done) single = false;
+                    const bool hop = lane < nh;
+                    const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
+                    if (pass == 0) amt = min(amt, __reduce_min_sync(kFull, frev));
+                    if ((pass == 0 && single && done) || pass == 1) {
+                        if (hop) {
+                            const unsigned bit = 1u << (pi & 31);
+                            const unsigned old = atomicOr(&cmask[pj * KR + (pi >> 5)], bit);
+                            int *f = flow + pi * ldc + pj;
+                            *f = (old & bit) ? *f + amt : amt;
+                            if (pjp >= 0) {
+                                flow[pi * ldc + pjp] = frev - amt;
+                                if (frev == amt) atomicAnd(&cmask[pjp * KR + (pi >> 5)], ~bit);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (single) break;
+            }
+            sup -= amt;
+            if (lane == jl) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
+            }
+        }
+    }
+    long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nc) {
+#pragma unroll
+            for (int w = 0; w < KR; ++w) {
+                unsigned bits = cmask[c * KR + w];
+                while (bits) {
+                    const int i = 32 * w + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    tot += (long long)flow[i * ldc + c] * (long long)cost[i * ldc + c];
+                }
+            }
+        }
+    }
+    return warp_sum_ll(tot);
+}
+
+template <int KR, int KC, bool GC>
+__global__ void __launch_bounds__(KR > 2 ? 128 : 256)
+emd_solve_multi_kernel(const __grid_constant__ SolveArgs A)
 {
     extern __shared__ __align__(16) int smem_i[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = solve_smem_per_warp(A.mr, A.mc, A.ldc, A.use_global) / 4;
-    int *sb = smem_i + (size_t)wib * per_warp;
-    int *su = sb, *srowdist = sb + A.mr, *srowpred = sb + 2 * A.mr, *ssupply = sb + 3 * A.mr;
-    int *sridx = sb + 4 * A.mr, *scidx = sb + 5 * A.mr, *sway = scidx + A.mc;
+    const int ldc = A.ldc;
+    int *sb = smem_i + (size_t)wib * (solve_multi_smem_per_warp<KR, KC>(A.mr, A.mc, ldc, GC) / 4);
+    int *sridx = sb, *scidx = sb + A.mr;
+    unsigned *cmask = reinterpret_cast<unsigned *>(scidx + A.mc);
     int *cost, *flow;
-    if (A.use_global) {
-        cost = A.scratch + ((size_t)blockIdx.x * wpb + wib) * 2 * (size_t)A.mr * A.ldc;
-        flow = cost + (size_t)A.mr * A.ldc;
-    } else {
-        cost = sway + A.mc;
-        flow = cost + (size_t)A.mr * A.ldc;
+    {
+        const size_t w = (size_t)blockIdx.x * wpb + wib, mat = (size_t)A.mr * ldc;
+        if (GC) { cost = A.scratch + w * 2 * mat; flow = cost + mat; }
+        else    { cost = reinterpret_cast<int *>(cmask + (size_t)A.mc * KR); flow = A.scratch + w * mat; }
     }
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 
     for (;;) {
-        int q0 = 0;
-        if (lane == 0) q0 = (int)atomicAdd(A.counter, kSolveClaim);
-        q0 = __shfl_sync(kFull, q0, 0);
-        if (q0 >= A.npairs) break;
-        const int q1 = min(A.npairs, q0 + (int)kSolveClaim);
-        for (int q = q0; q < q1; ++q) {
-            const int meta = A.meta[q];
-            const int cls = meta & 7;
-            const int64_t p = A.p0 + q;
-            if (cls == kClsNone) continue;                       // early-out already written by K1
-            if (cls != A.cls) continue;
-            const float maxc_f = A.maxc[q];
-            if (!(maxc_f > 0.f)) {                               // S4: all-zero distance matrix
-                if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
-                continue;
-            }
-            const int u = A.u12[q];
-            const int u1 = u & 0xffff, u2 = u >> 16;
-            const bool swap = (meta & kMetaSwap) != 0;
-            int64_t a1, a2; int l;
-            doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
-            const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
-            const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
-            const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
-            // compact the residual rows / columns
-            int m = 0, n = 0, sumR = 0, sumC = 0;
-            for (int base = 0; base < uR; base += kWarp) {
-                const int i = base + lane;
-                const int x = i < uR ? ipR[i] : 0;
-                const unsigned bal = __ballot_sync(kFull, x > 0);
-                if (x > 0) { const int pos = m + __popc(bal & ((1u << lane) - 1)); sridx[pos] = i; ssupply[pos] = x; }
-                m += __popc(bal);
-                sumR += x;
-            }
-            int deficit[KC];
+        int q = 0;
+        if (lane == 0) q = (int)atomicAdd(A.counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= A.npairs) break;
+        const int meta = A.meta[q];
+        if ((meta & 7) != A.cls) continue;
+        const int64_t p = A.p0 + q;
+        const float maxc_f = A.maxc[q];
+        if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+            continue;
+        }
+        const int uu = A.u12[q];
+        const int u1 = uu & 0xffff, u2 = uu >> 16;
+        const bool swap = (meta & kMetaSwap) != 0;
+        int64_t a1, a2; int l;
+        doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
+        const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
+        const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
+        const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
+        int m = 0, n = 0, sumR = 0, sumC = 0;
+        for (int base = 0; base < uR; base += kWarp) {           // compact the residual rows: (mass << 8) | index
+            const int i = base + lane;
+            const int x = i < uR ? ipR[i] : 0;
+            const unsigned bal = __ballot_sync(kFull, x > 0);
+            if (x > 0) sridx[m + __popc(bal & ((1u << lane) - 1))] = (x << 8) | i;
+            m += __popc(bal);
+            sumR += x;
+        }
+        for (int base = 0; base < uC; base += kWarp) {
+            const int j = base + lane;
+            const int x = j < uC ? ipC[j] : 0;
+            const unsigned bal = __ballot_sync(kFull, x > 0);
+            if (x > 0) scidx[n + __popc(bal & ((1u << lane) - 1))] = (x << 8) | j;
+            n += __popc(bal);
+            sumC += x;
+        }
+        sumR = warp_sum(sumR); sumC = warp_sum(sumC);
+        __syncwarp();
+        const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+        long long opt = 0;
+        if (n > 0 && m > 0) {
+            const int diff = sumR - sumC;                        // >= 0 by the choice of the supplying side
+            const int nc = n + (diff > 0 ? 1 : 0);
+            int supply[KR], deficit[KC], cj[KC];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) deficit[k] = 0;
-            for (int base = 0; base < uC; base += kWarp) {
-                const int j = base + lane;
-                const int x = j < uC ? ipC[j] : 0;
-                const unsigned bal = __ballot_sync(kFull, x > 0);
-                if (x > 0) { const int pos = n + __popc(bal & ((1u << lane) - 1)); scidx[pos] = j; sway[pos] = x; /* staging */ }
-                n += __popc(bal);
-                sumC += x;
+            for (int k = 0; k < KR; ++k) { const int i = lane + 32 * k; supply[k] = i < m ? sridx[i] >> 8 : 0; }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                const int pc = c < n ? scidx[c] : 0;
+                cj[k] = pc & 0xff;
+                deficit[k] = c < n ? pc >> 8 : (c == n ? diff : 0);
             }
-            sumR = warp_sum(sumR); sumC = warp_sum(sumC);
-            __syncwarp();
-            long long opt = 0;
-            if (n > 0 && m > 0) {
-                const int diff = sumR - sumC;                    // >= 0 by the choice of the supplying side
-                const int nc = n + (diff > 0 ? 1 : 0);
+            // quantised costs of the residual sub-tile (S6(d)); the dummy column costs 0
+            const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+            for (int rI = 0; rI < m; ++rI) {
+                const int i = sridx[rI] & 0xff;
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     const int c = lane + 32 * k;
-                    deficit[k] = c < n ? sway[c] : (c == n && diff > 0 ? diff : 0);
-                }
-                __syncwarp();
-                // quantised costs of the residual sub-tile (S6(d)); dummy column costs 0
-                const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
-                const float *tile = A.tiles + (int64_t)q * A.tile_stride;
-                for (int rI = 0; rI < m; ++rI) {
-                    const int i = sridx[rI];
-                    for (int c = lane; c < nc; c += kWarp) {
+                    if (c < nc) {
                         int ic = 0;
                         if (c < n) {
-                            const int j = scidx[c];
-                            const float dv = swap ? tile[(int64_t)j * u2 + i] : tile[(int64_t)i * u2 + j];
+                            const float dv = swap ? tile[(int64_t)cj[k] * u2 + i] : tile[(int64_t)i * u2 + cj[k]];
                             ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
                         }
-                        cost[rI * A.ldc + c] = ic;
+                        cost[rI * ldc + c] = ic;
                     }
                 }
-                __syncwarp();
-                opt = transport_solve<KC>(m, nc, A.ldc, cost, flow, su, srowdist, srowpred, ssupply, sway, deficit, lane);
-            }
-            if (lane == 0) {
-                const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
-                double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
-                dist = __ddiv_rn(dist, A.pqn[q]);                 // S6(f)
-                dist = __ddiv_rn(dist, Cn);
-                dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
-                A.out[p] = dist;
             }
             __syncwarp();
+            opt = transport_solve_multi<KR, KC>(m, nc, ldc, cost, flow, cmask, supply, deficit, lane);
         }
+        if (lane == 0) {
+            double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
+            dist = __ddiv_rn(dist, A.pqn[q]);                     // S6(f)
+            dist = __ddiv_rn(dist, Cn);
+            dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
+            A.out[p] = dist;
+        }
+        __syncwarp();
     }
 }
 

@@ -425,16 +425,23 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         S.tiles = W.tiles.as<float>(); S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
         S.counter = W.counters.as<unsigned int>() + cls;
         S.out = O.out; S.status = O.status;
+        const bool multi = cls != kClsA;
         int wpb = 8;
         size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
-                                       : solve_smem_per_warp(S.mr, S.mc, S.ldc, S.use_global);
+                        : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
+                                       : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
+        int blocks_per_sm = E->solve_blocks_per_sm;
+        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(4, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
+        if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
-        int grid = (int)std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * (cls == kClsC ? 2 : E->solve_blocks_per_sm));
+        const int ppw = multi ? 1 : 8;                                                    // pairs per warp below which the grid shrinks
+        int grid = (int)std::min<int64_t>(((int64_t)Bc + ppw * wpb - 1) / (ppw * wpb), (int64_t)E->sm_count * blocks_per_sm);
         grid = std::max(grid, 1);
         S.scratch = nullptr;
-        if (S.use_global) {
-            if ((rc = W.scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;
+        if (multi) {
+            // per warp: flow (class B; its costs sit in shared memory), cost + flow (class C)
+            if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
             S.scratch = W.scratch.as<int32_t>();
         }
         Prof pr(E, WMD_K_SOLVE, st);
@@ -442,11 +449,11 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             emd_solve_small_kernel<<<grid, wpb * 32, smem, st>>>(S);
         } else if (cls == kClsB) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_kernel<2><<<grid, wpb * 32, smem, st>>>(S);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_multi_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_multi_kernel<2, 2, false><<<grid, wpb * 32, smem, st>>>(S);
         } else {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_kernel<9><<<grid, wpb * 32, smem, st>>>(S);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_multi_kernel<8, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_multi_kernel<8, 9, true><<<grid, wpb * 32, smem, st>>>(S);
         }
         CK(cudaGetLastError());
     }

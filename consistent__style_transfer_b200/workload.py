@@ -9,6 +9,7 @@ tests, ``bench.py`` and the CPU baseline all see the same bytes.
 * ``yelp``  lengths ``1 + binomial(19, 0.45)`` (1..20, mean 9.55; real Yelp mean 9.2)
 * ``book``  lengths ``clip(1 + binomial(63, 0.22), 1, 64)`` (mean ~14.9; real book 14.6)
 * ``fixed:L`` both sides exactly L tokens (length sweep, BASELINE config 5)
+* ``uniform:A-B`` lengths uniform in [A, B], drawn per side (mixed solver classes and cost-stage kinds in one launch)
 * variant ``independent`` (doc2 drawn independently: worst case, little cancellation) or
   ``noised`` (doc2 = doc1 with each token moved w.p. 0.15 to a random other document of its
   batch of 256, after /root/reference/src/data_util.py:32-54).
@@ -39,6 +40,9 @@ def _lengths(rng, shape: str, B: int) -> np.ndarray:
         return np.clip(1 + rng.binomial(63, 0.22, size=B), 1, 64)
     if shape.startswith("fixed:"):
         return np.full(B, int(shape.split(":")[1]), dtype=np.int64)
+    if shape.startswith("uniform:"):
+        lo, hi = (int(x) for x in shape.split(":")[1].split("-"))
+        return rng.integers(lo, hi + 1, size=B)
     raise ValueError(shape)
 
 

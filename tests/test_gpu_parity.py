@@ -133,6 +133,23 @@ def test_length_sweep_matches_oracle(eng_mod, oracle, L):
     e.close()
 
 
+@pytest.mark.parametrize("shape,variant,V,d,B", [
+    # long documents over small vocabularies: unequal masses, partial cancellation, tied costs, residual problems
+    # of every solver class (A <= 32, B <= 64, C <= 256 rows) and packed as well as block-split cost stages in one launch
+    ("uniform:1-90", "independent", 3000, 300, 1500), ("uniform:1-256", "independent", 400, 64, 600), ("fixed:256", "independent", 300, 8, 200),
+    ("uniform:30-70", "noised", 150, 100, 800), ("fixed:100", "independent", 120, 32, 500),
+    ("fixed:200", "noised", 5000, 16, 300), ("uniform:40-45", "independent", 10000, 300, 1000),
+])
+def test_mixed_long_documents_match_oracle(eng_mod, oracle, shape, variant, V, d, B):
+    table = workload.make_table(V, d, seed=11)
+    ids1, off1, ids2, off2 = workload.make_pairs(B, shape, variant, V=V, seed=13)
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
+    _assert_wmd_equal(got, st, want, wst)
+    e.close()
+
+
 def test_rwmd_matches_oracle(eng_mod, oracle):
     V = 600
     table = workload.make_table(V, 100, seed=6)

@@ -28,10 +28,13 @@ CONFIGS = [
     ("fixed:33", "independent", 500, 40, False, 0.0),
     ("fixed:70", "independent", 3_000, 24, False, 0.0),
     ("fixed:200", "independent", 5_000, 12, False, 0.0),
+    ("uniform:1-100", "independent", 200, 300, False, 0.01),
+    ("uniform:20-200", "noised", 600, 20, True, 0.0),
+    ("uniform:33-64", "independent", 64, 48, False, 0.0),
 ]
 bad = 0
 for shape, variant, V, d, use_rank, oov in CONFIGS:
-    n = N if not shape.startswith("fixed:") or int(shape.split(":")[1]) < 30 else max(2000, N // 50)
+    n = max(2000, N // 50) if shape.startswith("uniform:") or (shape.startswith("fixed:") and int(shape.split(":")[1]) >= 30) else N
     rng = np.random.default_rng(hash((shape, variant, V, d)) % (2 ** 32))
     table = workload.make_table(V, d, seed=int(rng.integers(1 << 30)))
     ids1, off1, ids2, off2 = workload.make_pairs(n, shape, variant, V=V, seed=int(rng.integers(1 << 30)))
