@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs", "latency", "sweep"],
                     help="pairs = BASELINE configs[1] (the driver's headline); allpairs = configs[3], top-k with RWMD pruning")
+    ap.add_argument("--lengths", default="8,16,32,64,128,256", help="sweep: document lengths")
     ap.add_argument("--docs", type=int, default=100_000, help="allpairs: documents in the set (self join)")
     ap.add_argument("--topk", type=int, default=16)
     ap.add_argument("--verify", type=int, default=2000, help="allpairs: brute-force check of the first N x N block (0 = off)")
@@ -200,6 +201,13 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -324,11 +332,7 @@ def run_b200(a):
     same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     alg_bytes_step = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * a.pairs
     kern = {k: v for k, v in prof.items() if v["launches"] > 0}
     dom = max(kern, key=lambda k: kern[k]["ms"])
@@ -512,46 +516,71 @@ def run_latency(a):
 
 
 def run_sweep(a):
-    """BASELINE configs[4]: fixed document lengths 8 -> 256 (both sides, independent draws, d=300), 2^18 pairs each
-    (2^14 from 128 tokens up), device-resident inputs, CUDA-event timed; per-kernel times from a serialised pass."""
+    """BASELINE configs[4]: fixed document lengths 8 -> 256 (both sides, independent draws, d=300), 2^18 pairs per GPU
+    and length (2^14 from 128 tokens up), device-resident inputs, CUDA-event timed, max over ranks; the scores are
+    all-gathered over NCCL inside the timed region when N > 1.  Per-kernel times come from a serialised pass on rank 0."""
     import torch
+    import torch.distributed as dist
     from consistent__style_transfer_b200.engine import WMDEngine
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     table = workload.make_table(a.vocab, a.d, seed=0)
-    eng = WMDEngine(table, device=0)
+    eng = WMDEngine(table, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lengths = [int(x) for x in a.lengths.split(",")]
     rows = {}
-    for L in (8, 16, 32, 64, 128, 256):
+    for L in lengths:
         n = 1 << (18 if L < 128 else 14)
-        ids1, off1, ids2, off2 = workload.make_pairs(n, f"fixed:{L}", "independent", V=a.vocab, seed=L)
+        ids1, off1, ids2, off2 = workload.make_pairs(n, f"fixed:{L}", "independent", V=a.vocab, seed=L + 1000 * rank)
         d = [torch.from_numpy(x).to(dev) for x in (ids1, off1, ids2, off2)]
         out = torch.empty(n, dtype=torch.float64, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev)
-        for _ in range(3):
+        g_out = torch.empty(world * n, dtype=torch.float64, device=dev) if world > 1 else None
+
+        def step():
             eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
+            if world > 1:
+                dist.all_gather_into_tensor(g_out, out)
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         ms = []
         for _ in range(max(3, a.steps)):
             flush.fill_(1)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st); e1.record()
+            e0.record(); step(); e1.record()
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.median(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = float(t.item())
         stats = eng.last_stats()
         eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
         eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
         torch.cuda.synchronize()
         prof = eng.profile(reset=True)
         eng.set_profiling(False); eng.set_serial(False)
-        t = statistics.median(ms)
         alg = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * n
-        rows[str(L)] = {"pairs": n, "ms": t, "pairs_per_s": n / (t / 1e3), "mean_unique_tokens_per_side": stats["uniques"] / (2 * n),
-                        "algorithmic_gb_per_s": alg / (t / 1e3) / 1e9,
+        rows[str(L)] = {"pairs_per_gpu": n, "ms": t, "pairs_per_s": world * n / (t / 1e3),
+                        "mean_unique_tokens_per_side": stats["uniques"] / (2 * n),
+                        "algorithmic_gb_per_s_per_gpu": alg / (t / 1e3) / 1e9,
+                        "hbm_roofline_frac": alg / (t / 1e3) / 1e9 / hbm_peak()[0],
                         "kernel_ms_serial": {k: v["ms"] for k, v in prof.items() if v["launches"] > 0}}
-    print(json.dumps({"metric": "wmd_length_sweep_pairs_per_sec", "unit": "pairs/s", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": f"fixed lengths 8..256 both sides, independent, d={a.d}, V={a.vocab}",
-                                 "l2": "256 MiB flush write between timed steps"}, "lengths": rows}), flush=True)
+    if rank == 0:
+        print(json.dumps({"metric": "wmd_length_sweep_pairs_per_sec", "unit": "pairs/s", "n_gpus": world, "dtype": "f64", "data": "synthetic",
+                          "scaling": "weak",
+                          "config": {"workload": f"fixed lengths {a.lengths} both sides, independent, d={a.d}, V={a.vocab}, 2^18 pairs per GPU (2^14 from 128 tokens)",
+                                     "l2": "256 MiB flush write between timed steps",
+                                     "timing": "median of the timed steps per rank (CUDA events), max over ranks"},
+                          "peak_hbm_gbs": hbm_peak()[0], "lengths": rows}), flush=True)
     eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

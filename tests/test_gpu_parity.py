@@ -150,6 +150,40 @@ def test_mixed_long_documents_match_oracle(eng_mod, oracle, shape, variant, V, d
     e.close()
 
 
+def _chain_table(n, eps=0.002, h=0.2, d=8):
+    """Rows 0..n on a short arc of the unit circle, rows n+1..2n+1 the same arc lifted to latitude h: document
+    {1..n} against {n+1..2n} (lifted points 0..n-1) assigns point i to lifted point i until the last row finds only
+    lifted point 0 free, and the cheapest way there shifts every earlier assignment by one: an augmenting path of n hops."""
+    T = np.zeros((2 * n + 2, d), np.float32)
+    for i in range(n + 1):
+        T[i, :3] = [np.cos(i * eps), np.sin(i * eps), 0.0]
+        T[n + 1 + i, :3] = [np.cos(i * eps) * np.cos(h), np.sin(i * eps) * np.cos(h), np.sin(h)]
+    return T
+
+
+@pytest.mark.parametrize("n", [12, 31, 33, 64, 100, 200, 256])
+def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n):
+    # paths longer than 32 hops are walked in pieces by the class B / C solver (solve.cuh: transport_solve_multi)
+    table = _chain_table(n)
+    fwd = (np.arange(1, n + 1), n + 1 + np.arange(0, n))
+    docs1, docs2 = [], []
+    rng = np.random.default_rng(n)
+    for k in range(24):
+        a, b = fwd if k % 2 == 0 else fwd[::-1]
+        if k >= 2:                                                # variations: repeated tokens (unequal masses), dropped tokens
+            a = np.concatenate([a, rng.choice(a, size=rng.integers(0, 4))]) if len(a) < 250 else a
+            b = np.delete(b, rng.integers(0, len(b), size=rng.integers(0, 3)))
+        docs1.append(a.astype(np.int32)); docs2.append(b.astype(np.int32))
+    ids1, off1 = workload.to_csr(docs1)
+    ids2, off2 = workload.to_csr(docs2)
+    e = eng_mod.WMDEngine(table)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=4)
+    _assert_wmd_equal(got, st, want, wst)
+    assert np.array_equal(got, want)
+    e.close()
+
+
 def test_rwmd_matches_oracle(eng_mod, oracle):
     V = 600
     table = workload.make_table(V, 100, seed=6)
