@@ -16,8 +16,9 @@
 //     tile tasks from a shared counter, decode one descriptor (a single LDS.128) and run the
 //     2x4-cell leaf loops; a warp that finds no tiles left moves on and releases the stage through
 //     its "empty" barrier.
-// Pairs that do not fit a stage (u1 + u2 > R or more than 64 tile tasks: long documents) are left
-// to the general kernel in cost.cuh, which skips everything planned here.
+// Pairs that do not fit a stage (u1 + u2 > R or more than 64 tile tasks: long documents) are cut by the
+// plan into blocks of at most split_block_max(R) rows per side, every block a stage of its own; the
+// general kernel in cost.cuh only runs when this path is switched off.
 #pragma once
 #include <cstddef>
 #include "cost.cuh"

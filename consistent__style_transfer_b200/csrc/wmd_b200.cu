@@ -3,7 +3,7 @@
 // Pipeline per chunk of pairs (all on one CUDA stream, chunks alternate between two streams so
 // that the FP32-bound cost kernel of one chunk overlaps the latency-bound solver of the other
 // and the chunk's tiles stay L2-resident between the two):
-//     K1 nbow_pairs_kernel -> K2 cost_tiles_kernel (+ large variant) -> K3 emd_solve_kernel<KC>
+//     K1 nbow_pairs_kernel -> K2 cost_plan_kernel + cost_tiles_fast_kernel -> K3 emd_solve_small_kernel / emd_solve_multi_kernel
 // There is no CPU implementation behind this ABI: without a device every entry fails.
 #include "../../include/wmd_b200.h"
 
@@ -431,7 +431,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
                         : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
                                        : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
         int blocks_per_sm = E->solve_blocks_per_sm;
-        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(4, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
+        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
         if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
