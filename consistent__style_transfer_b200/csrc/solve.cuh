@@ -57,14 +57,45 @@ __host__ __device__ inline size_t solve_small_smem_per_warp(int mr, int mc, int 
     return ((size_t)2 * mr * ldc + mr + mc + 32) * 4;
 }
 
-__device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost, int *flow, unsigned *cmask,
+// Shared-memory accesses of the class-A solver go through 32-bit shared addresses: with generic
+// pointers the compiler rebuilt the CTA's shared window base (S2UR SR_CgaCtaId + UMOV + ULEA) in front
+// of every LDS of the select / expand / relax loop -- 4 % of the kernel's instructions.
+__device__ __forceinline__ unsigned smem_addr(const void *p)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));                                   // opaque: kept in a register, not rematerialised
+    return a;
+}
+__device__ __forceinline__ int lds32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, int v)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void atom_or_s32(unsigned a, unsigned v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void atom_and_s32(unsigned a, unsigned v)
+{
+    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost_p, int *flow_p, unsigned *cmask_p,
                                                            int supply, int deficit, int lane)
 {
+    const unsigned cost = smem_addr(cost_p), flow = smem_addr(flow_p), cmask = smem_addr(cmask_p);
+    const unsigned ld4 = (unsigned)ldc * 4u, lane4 = (unsigned)lane * 4u;
     int u = 0, v = 0;
-    for (int x = lane; x < m * ldc; x += kWarp) flow[x] = 0;
-    cmask[lane] = 0;
+    for (int x = lane; x < m * ldc; x += kWarp) sts32(flow + 4u * x, 0);
+    sts32(cmask + lane4, 0);
     __syncwarp();
     const bool iscol = lane < nc;
+    const unsigned lbit = 1u << lane;
     for (int r = 0; r < m; ++r) {
         int sup = __shfl_sync(kFull, supply, r);
         while (sup > 0) {
@@ -73,13 +104,13 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
             int minv = kIntInf, way = r;
             {
                 const int ur = __shfl_sync(kFull, u, r);
-                if (iscol) minv = cost[r * ldc + lane] - ur - v;
+                if (iscol) minv = lds32(cost + r * ld4 + lane4) - ur - v;
             }
-            int delta, jl, def;
-            for (;;) {
-                const int key = ((used >> lane) & 1u) ? kIntInf : minv;
-                delta = __reduce_min_sync(kFull, key);
-                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
+            int jl = 0, def = 0;
+            int key = minv;                                      // kIntInf once the column is used
+            int delta = __reduce_min_sync(kFull, key);
+            // the loop condition only fails on unbalanced input (cannot happen): never spin
+            while (delta < kIntInf) {
                 jl = __ffs(__ballot_sync(kFull, key == delta)) - 1;
                 used |= 1u << jl;
                 def = __shfl_sync(kFull, deficit, jl);
@@ -92,27 +123,36 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
                     // leave the loop and restart the search after the augmentation.
                     if (__shfl_sync(kFull, way, jl) != r) break;
                     const int amt = min(sup, def);
-                    if (lane == jl) { flow[r * ldc + jl] += amt; cmask[jl] |= 1u << r; deficit -= amt; }
+                    if (lane == jl) {
+                        const unsigned fa = flow + r * ld4 + lane4;
+                        sts32(fa, lds32(fa) + amt);
+                        sts32(cmask + lane4, lds32(cmask + lane4) | (1u << r));
+                        deficit -= amt;
+                    }
                     __syncwarp();
                     sup -= amt;
                     def -= amt;
                     if (sup == 0) break;                         // def may be > 0: the standard end of a search
                 }
-                unsigned nr = cmask[jl] & ~tree;                 // rows shipping into the saturated column
+                unsigned nr = (unsigned)lds32(cmask + 4u * jl) & ~tree;      // rows shipping into the saturated column
                 tree |= nr;
-                if ((nr >> lane) & 1u) { rdist = delta; rpred = jl; }
+                if (nr & lbit) { rdist = delta; rpred = jl; }
                 while (nr) {
                     const int i = __ffs(nr) - 1;
                     nr &= nr - 1;
                     const int ui = __shfl_sync(kFull, u, i);
-                    if (iscol && !((used >> lane) & 1u)) {
-                        const int cand = delta + cost[i * ldc + lane] - ui - v;
+                    if (iscol && !(used & lbit)) {
+                        const int cand = delta + lds32(cost + i * ld4 + lane4) - ui - v;
                         if (cand < minv) { minv = cand; way = i; }
                     }
                 }
+                key = (used & lbit) ? kIntInf : minv;
+                delta = __reduce_min_sync(kFull, key);
             }
-            if ((tree >> lane) & 1u) u += delta - rdist;         // dual update (tree nodes only)
-            if ((used >> lane) & 1u) v -= delta - minv;
+            asm volatile("" : "+r"(delta));                        // opaque: the error exit is tested here, once per search,
+            if (delta >= kIntInf) return -1;                     // not threaded into the loop's back edge (3 BREAKs per step)
+            if (tree & lbit) u += delta - rdist;                 // dual update (tree nodes only)
+            if (used & lbit) v -= delta - minv;
             if (sup == 0) break;                                 // the row emptied on a direct arc
             // tree path jl -> ... -> r, walked once: hop k = (row pi ships into column pj, and stops shipping
             // amt into its tree predecessor column pjp) lands in lane k
@@ -125,14 +165,15 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
                 j = jp;
             }
             const bool hop = lane < nh;
-            const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
+            const unsigned frow = flow + pi * ld4;
+            const int frev = (hop && pjp >= 0) ? lds32(frow + 4u * pjp) : kIntInf;
             const int amt = min(min(sup, def), __reduce_min_sync(kFull, frev));
             if (hop) {
-                flow[pi * ldc + pj] += amt;
-                atomicOr(&cmask[pj], 1u << pi);
+                sts32(frow + 4u * pj, lds32(frow + 4u * pj) + amt);
+                atom_or_s32(cmask + 4u * pj, 1u << pi);
                 if (pjp >= 0) {
-                    flow[pi * ldc + pjp] = frev - amt;
-                    if (frev == amt) atomicAnd(&cmask[pjp], ~(1u << pi));
+                    sts32(frow + 4u * pjp, frev - amt);
+                    if (frev == amt) atom_and_s32(cmask + 4u * pjp, ~(1u << pi));
                 }
             }
             __syncwarp();
@@ -142,7 +183,7 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
     }
     long long tot = 0;
     if (iscol)
-        for (int i = 0; i < m; ++i) tot += (long long)flow[i * ldc + lane] * (long long)cost[i * ldc + lane];
+        for (int i = 0; i < m; ++i) tot += (long long)lds32(flow + i * ld4 + lane4) * (long long)lds32(cost + i * ld4 + lane4);
     return warp_sum_ll(tot);
 }
 

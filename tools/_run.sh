@@ -1,13 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest45.log 2>&1; echo pytest rc=$?; tail -2 gpurun_out/pytest45.log
-python tools/stress_parity.py 400000 > gpurun_out/stress45.log 2>&1; echo stress rc=$?; tail -1 gpurun_out/stress45.log
-python bench.py > gpurun_out/bench45.json 2> gpurun_out/bench45.err; echo bench rc=$?
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/ref45.json 2> gpurun_out/ref45.err; echo ref rc=$?
-python bench.py --d 100 --no-cpu-baseline > gpurun_out/bench45_d100.json 2> gpurun_out/bench45_d100.err; echo d100 rc=$?
-python bench.py --variant noised --no-cpu-baseline > gpurun_out/bench45_noised.json 2> gpurun_out/bench45_noised.err; echo noised rc=$?
-python bench.py --shape book --variant noised --d 100 --no-cpu-baseline > gpurun_out/bench45_book.json 2> gpurun_out/bench45_book.err; echo book rc=$?
-python bench.py --mode latency > gpurun_out/latency45.json 2> gpurun_out/latency45.err; echo latency rc=$?
-python bench.py --mode sweep --steps 3 > gpurun_out/sweep45.json 2> gpurun_out/sweep45.err; echo sweep rc=$?
-python bench.py --pairs 262144 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain45.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches45.csv python bench.py --pairs 262144 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu45.log 2>&1; echo launches rc=$?
-ncu --set full --clock-control none --import-source on -k regex:'nbow_pairs|cost_plan|cost_tiles_fast|emd_solve_small' -c 4 -s 16 -o gpurun_out/prof_r01_final2 -f python bench.py --pairs 262144 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu45b.log 2>&1; echo ncufull rc=$?
-ncu --set full --clock-control none --import-source on -k regex:'cost_plan|cost_tiles_fast|emd_solve_multi' -c 3 -s 3 -o gpurun_out/prof_r01_final2_L64 -f python bench.py --mode sweep --lengths 64 --steps 1 > gpurun_out/ncu45c.log 2>&1; echo ncufull64 rc=$?
-ncu --set full --clock-control none --import-source on -k regex:'emd_solve_multi' -c 1 -s 1 -o gpurun_out/prof_r01_final2_L256 -f python bench.py --mode sweep --lengths 256 --steps 1 > gpurun_out/ncu45d.log 2>&1; echo ncufull256 rc=$?
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest46.log 2>&1; echo pytest rc=$?; tail -2 gpurun_out/pytest46.log
+python tools/stress_parity.py 100000 > gpurun_out/stress46.log 2>&1; echo stress rc=$?; tail -1 gpurun_out/stress46.log
+python bench.py --no-cpu-baseline > gpurun_out/bench46.json 2> gpurun_out/bench46.err; echo bench rc=$?
