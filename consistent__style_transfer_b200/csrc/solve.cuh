@@ -251,22 +251,31 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
                 const int nc = n + (diff > 0 ? 1 : 0);
                 const int packedR = lane < m ? sridx[lane] : 0;
                 const int packedC = lane < n ? scidx[lane] : 0;
-                const int supply = packedR >> 8;
-                const int deficit = lane < n ? (packedC >> 8) : (lane == n ? diff : 0);
-                // quantised costs of the residual sub-tile (S6(d)); the dummy column costs 0
+                // The balanced problem is symmetric, so the solver's rows may be either side.  Rows = the side with
+                // MORE nodes: a search then wades through fewer columns before it meets one with a deficit
+                // (Yelp-shape pairs: 70 -> 50 column selections per pair; profiles/README.md).  flip: rows = the
+                // lighter side plus the surplus as a zero-cost dummy ROW, columns = the supplying side.
+                const bool flip = m < nc;
+                const int mm = flip ? nc : m, ncc = flip ? m : nc;
+                const int nrow = flip ? n : m, ncol = flip ? m : n;              // real (non-dummy) rows / columns
+                const int rowP = flip ? packedC : packedR, colP = flip ? packedR : packedC;
+                const int supply = lane < nrow ? (rowP >> 8) : ((flip && lane == nrow) ? diff : 0);
+                const int deficit = lane < ncol ? (colP >> 8) : ((!flip && lane == ncol) ? diff : 0);
+                // quantised costs of the residual sub-tile (S6(d)); the dummy row / column costs 0
                 const float *tile = A.tiles + (int64_t)q * A.tile_stride;
-                const int j = packedC & 0xff;
-                for (int rI = 0; rI < m; ++rI) {
-                    const int i = __shfl_sync(kFull, packedR, rI) & 0xff;
+                const int cidx = colP & 0xff;
+                const bool rows_doc1 = swap == flip;                             // the rows are doc1's tokens
+                for (int rI = 0; rI < mm; ++rI) {
+                    const int ridx = __shfl_sync(kFull, rowP, rI) & 0xff;
                     int ic = 0;
-                    if (lane < n) {
-                        const float dv = swap ? tile[j * u2 + i] : tile[i * u2 + j];
+                    if (lane < ncol && rI < nrow) {
+                        const float dv = rows_doc1 ? tile[ridx * u2 + cidx] : tile[cidx * u2 + ridx];
                         ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
                     }
-                    if (lane < nc) cost[rI * ldc + lane] = ic;
+                    if (lane < ncc) cost[rI * ldc + lane] = ic;
                 }
                 __syncwarp();
-                opt = transport_solve_small(m, nc, ldc, cost, flow, cmask, supply, deficit, lane);
+                opt = transport_solve_small(mm, ncc, ldc, cost, flow, cmask, supply, deficit, lane);
             }
             if (lane == 0) {
                 double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;

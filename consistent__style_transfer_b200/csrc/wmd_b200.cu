@@ -419,6 +419,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
         const int cap = cls == kClsA ? 32 : (cls == kClsB ? 64 : kMaxDocLen + 1);
         S.mr = std::min(cap, ML); S.mc = std::min(cap, ML + 1);
+        if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
         S.ldc = S.mc | 1;
         S.use_global = cls == kClsC;
         S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
