@@ -493,4 +493,53 @@ cost_tiles_fast_kernel(const __grid_constant__ FastArgs A)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2 from the word-distance table (optional, wmd_set_distance_table): with D[V][V] resident (built once per
+// embedding table by the kernels above, so every entry is bit-identical to what they would compute for
+// the pair) a pair's tile is a gather of u1 x u2 floats -- 4 bytes per cell from HBM / L2 instead of
+// 3 d rounded FP32 operations.  One warp per pair; the tile and its maximum land where K2b puts them.
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    DocSide s1, s2;
+    int64_t p0;
+    int32_t npairs;
+    int32_t _pad;
+    const int32_t *rows1, *rows2, *u12;
+    const float *D;
+    int64_t V;
+    float *tiles;
+    int64_t tile_stride;
+    unsigned int *maxc;
+};
+
+__global__ void __launch_bounds__(256)
+cost_gather_kernel(const __grid_constant__ GatherArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    int64_t tok1, tok2;
+    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
+    for (int q = gw; q < A.npairs; q += nw) {
+        const int u = A.u12[q];
+        const int u1 = u & 0xffff, u2 = u >> 16;
+        if (u1 == 0 || u2 == 0) continue;
+        int64_t a1, a2; int l;
+        doc_span(A.s1, A.p0 + q, a1, l); doc_span(A.s2, A.p0 + q, a2, l);
+        const int32_t *r1 = A.rows1 + slot_off(A.s1, tok1, q, a1), *r2 = A.rows2 + slot_off(A.s2, tok2, q, a2);
+        float *tile = A.tiles + (int64_t)q * A.tile_stride;
+        const int ncell = u1 * u2;
+        const float inv = 1.0f / (float)u2;
+        unsigned mx = 0;
+        for (int c = lane; c < ncell; c += kWarp) {
+            const int i = (int)(((float)c + 0.5f) * inv);         // c / u2: exact for c < 2^16, u2 <= 256
+            const int j = c - i * u2;
+            const float v = __ldg(A.D + (int64_t)__ldg(r1 + i) * A.V + __ldg(r2 + j));
+            tile[c] = v;
+            mx = max(mx, __float_as_uint(v));                      // distances are >= 0: uint order == float order
+        }
+        mx = __reduce_max_sync(kFull, mx);
+        if (lane == 0) A.maxc[q] = mx;
+    }
+}
+
 }  // namespace wmd

@@ -107,6 +107,7 @@ struct wmd_engine {
     Workspace ws[2];
     // all-pairs mode (allpairs.cuh): V x V distance table (lazy) and a grow-only workspace
     float *dtab = nullptr;
+    bool use_dtab = false;                       // pair path takes its tiles from dtab (wmd_set_distance_table)
     float dmax = 0.f;
     cudaStream_t ap_stream = nullptr;
     DevBuf ap[32];
@@ -274,8 +275,21 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
                 const int32_t *u12, float *tiles, int64_t tile_stride, unsigned int *maxc)
 {
     int rc;
-    const Vocab vc = make_vocab(E);
     if ((rc = W.counters.ensure(64))) return rc;
+    if (E->use_dtab && E->dtab) {                        // tiles gathered from the word-distance table
+        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));    // K3's work-claim counters
+        CK(cudaMemsetAsync(maxc, 0, (size_t)Bc * 4, st));
+        GatherArgs G;
+        G.s1 = s1; G.s2 = s2; G.p0 = p0; G.npairs = Bc; G._pad = 0;
+        G.rows1 = rows1; G.rows2 = rows2; G.u12 = u12;
+        G.D = E->dtab; G.V = E->V; G.tiles = tiles; G.tile_stride = tile_stride; G.maxc = maxc;
+        const int grid = (int)std::min<int64_t>(((int64_t)Bc + 7) / 8, (int64_t)E->sm_count * 8);
+        Prof pr(E, WMD_K_COST, st);
+        cost_gather_kernel<<<std::max(grid, 1), 256, 0, st>>>(G);
+        CK(cudaGetLastError());
+        return WMD_OK;
+    }
+    const Vocab vc = make_vocab(E);
     {
         CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
         CK(cudaMemsetAsync(maxc, 0, (size_t)Bc * 4, st));
@@ -917,6 +931,13 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         normalize_rows_kernel<<<(unsigned)((V + 127) / 128), 128>>>(E->table, V, d, E->ld, E->plan);
         if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(WMD_ECUDA, "normalize failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
+    if (const char *v = getenv("WMD_DTAB")) {             // WMD_DTAB=1: pair entries gather their tiles from the V x V table
+        if (atoi(v)) {
+            int rc;
+            if ((rc = ensure_dtab(E, E->streams[0]))) return bail(rc);
+            E->use_dtab = true;
+        }
+    }
     *out = E;
     return WMD_OK;
 }
@@ -1142,6 +1163,17 @@ int wmd_set_serial(wmd_handle E, int32_t enabled)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
     E->slot_mask = enabled ? 0 : 1;
+    return WMD_OK;
+}
+
+int wmd_set_distance_table(wmd_handle E, int32_t enabled)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (!enabled) { E->use_dtab = false; return WMD_OK; }
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if ((rc = ensure_dtab(E, E->streams[0]))) return rc;
+    E->use_dtab = true;
     return WMD_OK;
 }
 

@@ -246,6 +246,11 @@ class WMDEngine:
         """One internal stream instead of two: per-kernel event times without co-scheduling effects."""
         _lib.check(self._L.wmd_set_serial(self._handle(), int(bool(enabled))))
 
+    def set_distance_table(self, enabled: bool = True):
+        """Build (once) the V x V float32 word-distance table and let the pair entries gather their cost tiles
+        from it instead of recomputing them (V * V * 4 bytes of device memory; results are bit-identical)."""
+        _lib.check(self._L.wmd_set_distance_table(self._handle(), int(bool(enabled))))
+
     def profile(self, reset: bool = True):
         ms = (ctypes.c_double * len(KERNEL_KINDS))()
         n = (ctypes.c_int64 * len(KERNEL_KINDS))()

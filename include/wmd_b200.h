@@ -146,6 +146,15 @@ int wmd_allpairs_topk_host(wmd_handle h, const int32_t *idsA, const int64_t *off
                            int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist,
                            int64_t *stats, double *ms);
 
+/* Optional word-distance table for the pair entries (additive; the reference has no counterpart: gensim's
+ * wmdistance, models/keyedvectors.py [gensim 3.8], recomputes every word distance per call, as the default path
+ * here does).  enabled != 0 builds, once per handle, the float32 distance of every two rows of the embedding
+ * table -- V * V * 4 bytes of device memory, computed by the pair path's own cost kernels, so each entry is
+ * bit-identical to what they produce for a pair -- and lets every later pair call gather its cost tiles from it
+ * instead of recomputing them.  Results do not change.  WMD_ENOMEM when the table does not fit.  The all-pairs
+ * entry builds and uses the same table on its own.  enabled == 0 returns to the direct path (the table is kept). */
+int wmd_set_distance_table(wmd_handle h, int32_t enabled);
+
 /* instrumentation ----------------------------------------------------------------------------- */
 
 /* When enabled, every kernel launch is bracketed by CUDA events on its own stream. */

@@ -184,6 +184,35 @@ def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n):
     e.close()
 
 
+@pytest.mark.parametrize("shape,variant,V,d,B,rank", [
+    ("yelp", "independent", 3000, 300, 3000, False), ("yelp", "noised", 500, 100, 3000, True),
+    ("book", "independent", 2000, 64, 1000, False), ("uniform:1-120", "independent", 700, 300, 400, False),
+    ("fixed:256", "independent", 900, 24, 60, True),
+])
+def test_distance_table_path_is_bit_identical(eng_mod, oracle, shape, variant, V, d, B, rank):
+    # wmd_set_distance_table: tiles gathered from the V x V table instead of recomputed; same bits as the direct path and the oracle
+    table = workload.make_table(V, d, seed=21)
+    ids1, off1, ids2, off2 = workload.make_pairs(B, shape, variant, V=V, seed=23)
+    rng = np.random.default_rng(3)
+    ids2 = ids2.copy(); ids2[rng.random(len(ids2)) < 0.02] = -1
+    rk = rng.permutation(V).astype(np.int32) if rank else None
+    e = eng_mod.WMDEngine(table, rank=rk)
+    direct, st0 = e.wmd_pairs(ids1, off1, ids2, off2)
+    e.set_distance_table(True)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    lb_t = e.rwmd_pairs(ids1, off1, ids2, off2)
+    e.set_distance_table(False)
+    again, st2 = e.wmd_pairs(ids1, off1, ids2, off2)
+    lb_d = e.rwmd_pairs(ids1, off1, ids2, off2)
+    assert got.tobytes() == direct.tobytes() == again.tobytes()
+    assert np.array_equal(st, st0) and np.array_equal(st2, st0)
+    for k in lb_t:
+        assert np.asarray(lb_t[k]).tobytes() == np.asarray(lb_d[k]).tobytes(), k
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, rank=rk, nthreads=8)
+    _assert_wmd_equal(got, st, want, wst)
+    e.close()
+
+
 def test_rwmd_matches_oracle(eng_mod, oracle):
     V = 600
     table = workload.make_table(V, 100, seed=6)
