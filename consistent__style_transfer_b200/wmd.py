@@ -137,8 +137,20 @@ class KeyedVectors:
         if e is None:
             e = WMDEngine(self.vectors, normalize=False, device=self.device, rank=self._rank,
                           token_map=self.token_map(tokenizer))
+            if getattr(self, "_distance_table", False):
+                e.set_distance_table(True)
             self._dev_engines[key] = e
         return e
+
+    def enable_distance_table(self, enabled: bool = True):
+        """New, additive: precompute the V x V word-distance table once (V * V * 4 bytes on the device) and let every
+        later ``wmdistance`` / ``cal_wmd_label`` / ``calculate_wmd_scores`` call look its cost tiles up instead of
+        recomputing them -- worth it for a scorer that lives as long as a training or evaluation run.  Values are
+        bit-identical (``include/wmd_b200.h``: ``wmd_set_distance_table``)."""
+        self._distance_table = bool(enabled)
+        self._engine.set_distance_table(enabled)
+        for e in self._dev_engines.values():
+            e.set_distance_table(enabled)
 
     def close(self):
         self._engine.close()

@@ -45,6 +45,17 @@ def test_calculate_wmd_scores_matches_golden(cases):
         model.wv.close()
 
 
+def test_distance_table_keeps_the_golden_values(cases):
+    # KeyedVectors.enable_distance_table: looked-up cost tiles, same golden bits (real text of the reference)
+    from consistent__style_transfer_b200 import content_preserve as cp
+    for c in cases:
+        model = cp.model_from_embeddings(c["vocab"], c["raw_vectors"], normalize=True)
+        model.wv.enable_distance_table()
+        got = cp.calculate_wmd_scores(c["text1"], c["text2"], model)
+        assert same_floats(got, c["wmd"]), c["name"]
+        model.wv.close()
+
+
 def test_load_word2vec_model_from_files(tmp_path, cases):
     from consistent__style_transfer_b200 import content_preserve as cp, gensim_pickle, wmd
     c = cases[2]
