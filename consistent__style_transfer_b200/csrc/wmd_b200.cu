@@ -446,6 +446,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
                         : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
                                        : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
         int blocks_per_sm = E->solve_blocks_per_sm;
+        if (cls == kClsA) { wpb = 4; blocks_per_sm *= 2; }                                // __launch_bounds__(128, 9)
         if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
         if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
