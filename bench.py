@@ -336,51 +336,60 @@ def run_b200(a):
     # from a V x V float32 table built once per embedding table instead of recomputed for every pair --------------
     wdt = None
     if not a.no_table_arm:
-        ref_out = d_out.clone()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        eng.set_distance_table(True)                                       # builds the table (host-synchronous)
-        build_s = time.perf_counter() - t0
-        for _ in range(a.warmup):
-            flush.fill_(1)
-            dev_step()
-        barrier()
-        eng.set_profiling(True); eng.profile(reset=True)
-        evs = []
-        for _ in range(a.steps):
-            flush.fill_(1)
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); dev_step(); e1.record()
-            evs.append((e0, e1))
-        barrier()
-        prof_t = eng.profile(reset=True)
-        eng.set_profiling(False)
-        tt = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], dtype=torch.float64, device=dev)
-        same_t = bool(torch.equal(ref_out.view(torch.int64), d_out.view(torch.int64)))
-        for _ in range(a.warmup):
-            host_step()
-        barrier()
-        e2e_t = 0.0
-        for _ in range(a.steps):
-            flush.fill_(1)
+        try:
+            ref_out = d_out.clone()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            host_step()
-            e2e_t += time.perf_counter() - t0
-        barrier()
-        te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        eng.set_distance_table(False)
-        wdt = {"value": n_gpus * a.pairs * a.steps / (float(tt.item()) / 1e3), "unit": UNIT,
-               "ms_per_step": float(tt.item()) / a.steps,
-               "e2e_value": n_gpus * a.pairs * a.steps / float(te.item()),
-               "table_bytes": int(a.vocab) * int(a.vocab) * 4, "table_build_ms_once": build_s * 1e3,
-               "bit_identical_to_direct_path": same_t,
-               "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof_t.items() if v["launches"] > 0},
-               "note": "wmd_set_distance_table(1): every word distance precomputed once per embedding table by the same cost kernels "
-                       "(bit-identical entries), pair tiles gathered from it; the build is outside these timed steps and is NOT part of "
-                       "the headline value / e2e above, which recompute every distance as the reference does"}
+            eng.set_distance_table(True)                                       # builds the table (host-synchronous)
+            build_s = time.perf_counter() - t0
+            for _ in range(a.warmup):
+                flush.fill_(1)
+                dev_step()
+            barrier()
+            eng.set_profiling(True); eng.profile(reset=True)
+            evs = []
+            for _ in range(a.steps):
+                flush.fill_(1)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); dev_step(); e1.record()
+                evs.append((e0, e1))
+            barrier()
+            prof_t = eng.profile(reset=True)
+            eng.set_profiling(False)
+            tt = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], dtype=torch.float64, device=dev)
+            same_t = bool(torch.equal(ref_out.view(torch.int64), d_out.view(torch.int64)))
+            for _ in range(a.warmup):
+                host_step()
+            barrier()
+            e2e_t = 0.0
+            for _ in range(a.steps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                host_step()
+                e2e_t += time.perf_counter() - t0
+            barrier()
+            te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            eng.set_distance_table(False)
+            wdt = {"value": n_gpus * a.pairs * a.steps / (float(tt.item()) / 1e3), "unit": UNIT,
+                   "ms_per_step": float(tt.item()) / a.steps,
+                   "e2e_value": n_gpus * a.pairs * a.steps / float(te.item()),
+                   "table_bytes": int(a.vocab) * int(a.vocab) * 4, "table_build_ms_once": build_s * 1e3,
+                   "bit_identical_to_direct_path": same_t,
+                   "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof_t.items() if v["launches"] > 0},
+                   "note": "wmd_set_distance_table(1): every word distance precomputed once per embedding table by the same cost kernels "
+                           "(bit-identical entries), pair tiles gathered from it; the build is outside these timed steps and is NOT part of "
+                           "the headline value / e2e above, which recompute every distance as the reference does"}
+        except Exception as exc:                                           # the additional arm must never cost the headline
+            if world > 1:
+                raise
+            try:
+                eng.set_distance_table(False)
+            except Exception:
+                pass
+            wdt = {"error": str(exc)[:200]}
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
     peak, peak_src = hbm_peak()

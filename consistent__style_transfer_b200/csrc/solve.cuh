@@ -372,21 +372,66 @@ __device__ long long transport_solve_multi(int m, int nc, int ldc, const int *co
                 for (int k = 0; k < KC; ++k) if (k == jk) used[k] |= 1u << jl;
                 def = __shfl_sync(kFull, sel_word<KC>(deficit, jk), jl);
                 if (def > 0) {
-                    // direct arc out of the root row: ship and keep searching (see transport_solve_small)
-                    if (__shfl_sync(kFull, sel_word<KC>(way, jk), jl) != r) break;
-                    const int amt = min(sup, def);
+                    // ship along the tree path and keep searching while the tree stays intact (see transport_solve_small)
+                    int amt;
+                    bool intact = true;
+                    if (__shfl_sync(kFull, sel_word<KC>(way, jk), jl) == r) {
+                        amt = min(sup, def);
+                        if (lane == jl) {
+                            const unsigned w = cmask[j0 * KR + rk];
+                            int *f = flow + r * ldc + j0;
+                            *f = (w >> rl) & 1u ? *f + amt : amt;
+                            cmask[j0 * KR + rk] = w | (1u << rl);
+                        }
+                    } else {
+                        // tree path j0 -> ... -> r in pieces of 32 hops (hop h = row pi starts shipping into column pj
+                        // and stops shipping amt into its tree predecessor column pjp); pass 0 finds the bottleneck, the
+                        // push follows at once when the path fits one piece, otherwise pass 1 walks it again
+                        int bott = kIntInf;
+                        amt = min(sup, def);
+                        for (int pass = 0; pass < 2; ++pass) {
+                            int j = j0;
+                            bool done = false, single = true;
+                            while (!done) {
+                                int pi = 0, pj = 0, pjp = -1, nh = 0;
+                                for (; nh < kWarp;) {
+                                    const int i = __shfl_sync(kFull, sel_word<KC>(way, j >> 5), j & 31);
+                                    const int jp = __shfl_sync(kFull, sel_word<KR>(rpred, i >> 5), i & 31);
+                                    if (lane == nh) { pi = i; pj = j; pjp = i == r ? -1 : jp; }
+                                    ++nh;
+                                    if (i == r) { done = true; break; }
+                                    j = jp;
+                                }
+                                if (!done) single = false;
+                                const bool hop = lane < nh;
+                                const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
+                                if (pass == 0) { bott = min(bott, __reduce_min_sync(kFull, frev)); amt = min(amt, bott); }
+                                if ((pass == 0 && single && done) || pass == 1) {
+                                    if (hop) {
+                                        const unsigned bit = 1u << (pi & 31);
+                                        const unsigned old = atomicOr(&cmask[pj * KR + (pi >> 5)], bit);
+                                        int *f = flow + pi * ldc + pj;
+                                        *f = (old & bit) ? *f + amt : amt;
+                                        if (pjp >= 0) {
+                                            flow[pi * ldc + pjp] = frev - amt;
+                                            if (frev == amt) atomicAnd(&cmask[pjp * KR + (pi >> 5)], ~bit);
+                                        }
+                                    }
+                                    __syncwarp();
+                                }
+                            }
+                            if (single) break;
+                        }
+                        intact = amt < bott;                     // no reverse arc of the path ran empty
+                    }
                     if (lane == jl) {
-                        const unsigned w = cmask[j0 * KR + rk];
-                        int *f = flow + r * ldc + j0;
-                        *f = (w >> rl) & 1u ? *f + amt : amt;
-                        cmask[j0 * KR + rk] = w | (1u << rl);
 #pragma unroll
                         for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
                     }
                     __syncwarp();
                     sup -= amt;
                     def -= amt;
-                    if (sup == 0) break;
+                    if (sup == 0 || !intact) break;              // the row is empty, or the search has to start again
                 }
                 // rows shipping into the saturated column join the tree at distance delta
 #pragma unroll
@@ -414,49 +459,6 @@ __device__ long long transport_solve_multi(int m, int nc, int ldc, const int *co
             for (int k = 0; k < KR; ++k) if (tree[k] & lbit) u[k] += delta - rdist[k];     // dual update (tree nodes only)
 #pragma unroll
             for (int k = 0; k < KC; ++k) if (used[k] & ~inval[k] & lbit) v[k] -= delta - minv[k];
-            if (sup == 0) break;                                 // the row emptied on a direct arc
-            // tree path j0 -> ... -> r in pieces of 32 hops (hop h = row pi starts shipping into column pj and
-            // stops shipping amt into its tree predecessor column pjp); pass 0 finds the bottleneck, the
-            // push follows at once when the path fits one piece, otherwise pass 1 walks it again
-            int amt = min(sup, def);
-            for (int pass = 0; pass < 2; ++pass) {
-                int j = j0;
-                bool done = false, single = true;
-                while (!done) {
-                    int pi = 0, pj = 0, pjp = -1, nh = 0;
-                    for (; nh < kWarp;) {
-                        const int i = __shfl_sync(kFull, sel_word<KC>(way, j >> 5), j & 31);
-                        const int jp = __shfl_sync(kFull, sel_word<KR>(rpred, i >> 5), i & 31);
-                        if (lane == nh) { pi = i; pj = j; pjp = i == r ? -1 : jp; }
-                        ++nh;
-                        if (i == r) { done = true; break; }
-                        j = jp;
-                    }
-                    if (!done) single = false;
-                    const bool hop = lane < nh;
-                    const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
-                    if (pass == 0) amt = min(amt, __reduce_min_sync(kFull, frev));
-                    if ((pass == 0 && single && done) || pass == 1) {
-                        if (hop) {
-                            const unsigned bit = 1u << (pi & 31);
-                            const unsigned old = atomicOr(&cmask[pj * KR + (pi >> 5)], bit);
-                            int *f = flow + pi * ldc + pj;
-                            *f = (old & bit) ? *f + amt : amt;
-                            if (pjp >= 0) {
-                                flow[pi * ldc + pjp] = frev - amt;
-                                if (frev == amt) atomicAnd(&cmask[pjp * KR + (pi >> 5)], ~bit);
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (single) break;
-            }
-            sup -= amt;
-            if (lane == jl) {
-#pragma unroll
-                for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
-            }
         }
     }
     long long tot = 0;
