@@ -131,3 +131,19 @@ def test_exact_lp_oracle_close_to_quantised(oracle):
         else:
             assert lp == q[p]
     assert 0.0 < worst < 3e-5
+
+
+def test_workload_shapes_are_deterministic_and_in_range():
+    # bench.py, the tests and the CPU baseline must all see the same bytes for a (shape, variant, seed)
+    for shape, lo, hi in (("yelp", 1, 20), ("book", 1, 64), ("fixed:37", 37, 37), ("uniform:3-90", 3, 90)):
+        a = workload.make_pairs(300, shape, "independent", V=500, seed=4)
+        b = workload.make_pairs(300, shape, "independent", V=500, seed=4)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+        for off in (a[1], a[3]):
+            lens = np.diff(off)
+            assert off[0] == 0 and lens.min() >= lo and lens.max() <= hi
+        assert a[0].dtype == np.int32 and a[1].dtype == np.int64
+        assert a[0].min() >= 0 and a[0].max() < 500
+    n1 = workload.make_pairs(256, "yelp", "noised", V=500, seed=4)
+    assert np.diff(n1[3]).sum() == np.diff(n1[1]).sum()          # transfer_noise moves tokens, it never drops them
