@@ -45,6 +45,7 @@ SIGNATURES = {
     "wmd_set_profiling": (ctypes.c_int, [c_handle, ctypes.c_int32]),
     "wmd_set_serial": (ctypes.c_int, [c_handle, ctypes.c_int32]),
     "wmd_set_distance_table": (ctypes.c_int, [c_handle, ctypes.c_int32]),
+    "wmd_distance_table_info": (ctypes.c_int, [c_handle, c_i64p, c_f64p, c_i32p, c_i32p]),
     "wmd_get_profile": (ctypes.c_int, [c_handle, c_f64p, c_i64p, ctypes.c_int32]),
     "wmd_get_last_stats": (ctypes.c_int, [c_handle, c_i64p]),
 }

@@ -84,8 +84,10 @@ __host__ __device__ inline size_t nbow_smem_per_warp(int Lp) { return (size_t)Lp
 
 __global__ void __launch_bounds__(256)
 nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, int32_t Lp,
-                  PairWork w, double *out, int32_t *status)
+                  PairWork w, double *out, int32_t *status, const int32_t *list, const unsigned int *nlist)
 {
+    // list mode (list != nullptr): the launch serves the *nlist pairs list[0..) of the chunk instead of all of them
+    if (nlist) npairs = (int32_t)*nlist;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -110,7 +112,8 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
     unsigned long long st_tok = 0, st_unq = 0, st_cells = 0, st_solved = 0;
     int st_mr = 0, st_mc = 0;
 
-    for (int q = blockIdx.x * wpb + wib; q < npairs; q += gridDim.x * wpb) {
+    for (int qq = blockIdx.x * wpb + wib; qq < npairs; qq += gridDim.x * wpb) {
+        const int q = list ? list[qq] : qq;
         const int64_t p = p0 + q;
         int64_t a1, a2; int n1raw, n2raw;
         doc_span(s1, p, a1, n1raw);

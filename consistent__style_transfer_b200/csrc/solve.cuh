@@ -39,7 +39,30 @@ struct SolveArgs {
     unsigned int *counter;            // work-claim counter for this launch (zeroed by the host)
     double *out;
     int32_t *status;
+    // list mode: the launch serves the *nlist pairs list[0..) of the chunk (fused.cuh leaves them behind)
+    const int32_t *list;
+    const unsigned int *nlist;
+    // gather mode (template flag GATHER): no cost tiles exist; costs come straight from the V x V word-distance
+    // table through the pairs' unique rows (K1), and the kernel finds maxC itself (kept in maxc_w for the epilogue)
+    const float *D;
+    int64_t V;
+    const int32_t *rows1, *rows2;
+    float *maxc_w;
 };
+
+// Largest entry of the u1 x u2 tile of D addressed by the unique rows r1 / r2 (pyemd's maxC is over the FULL matrix).
+__device__ __forceinline__ float gather_tile_max(const float *D, int64_t V, const int32_t *r1, const int32_t *r2, int u1, int u2, int lane)
+{
+    unsigned mx = 0;
+    const int ncell = u1 * u2;
+    const float inv = 1.0f / (float)u2;
+    for (int c = lane; c < ncell; c += kWarp) {
+        const int i = (int)(((float)c + 0.5f) * inv);                // c / u2: exact for c < 2^16, u2 <= 256
+        const int j = c - i * u2;
+        mx = max(mx, __float_as_uint(__ldg(D + (int64_t)__ldg(r1 + i) * V + __ldg(r2 + j))));
+    }
+    return __uint_as_float(__reduce_max_sync(kFull, mx));            // distances are >= 0: uint order == float order
+}
 
 // ------------------------------------------------------------------------------------------------
 // Class A (m <= 32 rows, nc <= 32 columns incl. the dummy): the same primal-dual method with the
@@ -193,6 +216,7 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
 // Everything the pair's set-up needs (offsets, the cost normaliser) dies before the solver runs: the solver's own
 // state fills the 48 registers that let five blocks of eight warps share an SM (at 64 registers the kernel ran 8 %
 // fewer instructions 5 % slower: 47 % instead of 58 % resident warps, 75 % instead of 85 % issue slots used).
+template <bool GATHER>
 __global__ void __launch_bounds__(128, 9)
 emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
 {
@@ -205,14 +229,26 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
     int *scidx = sridx + A.mr;
     unsigned *cmask = reinterpret_cast<unsigned *>(scidx + A.mc);
 
+    const int npairs = A.nlist ? (int)*A.nlist : A.npairs;
     for (;;) {
         int q = 0;
         if (lane == 0) q = (int)atomicAdd(A.counter, 1u);
         q = __shfl_sync(kFull, q, 0);
-        if (q >= A.npairs) break;
+        if (q >= npairs) break;
+        if (A.list) q = A.list[q];
         const int meta = A.meta[q];
         if ((meta & 7) != kClsA) continue;
-        const float maxc_f = A.maxc[q];
+        float maxc_f = 0.f;
+        if (!GATHER) maxc_f = A.maxc[q];
+        else {
+            const int uu = A.u12[q];
+            int64_t tok1, tok2, a1, a2; int l;
+            doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l);
+            doc_span(A.s1, A.p0 + q, a1, l); doc_span(A.s2, A.p0 + q, a2, l);
+            maxc_f = gather_tile_max(A.D, A.V, A.rows1 + slot_off(A.s1, tok1, q, a1), A.rows2 + slot_off(A.s2, tok2, q, a2),
+                                     uu & 0xffff, uu >> 16, lane);
+            if (lane == 0) A.maxc_w[q] = maxc_f;
+        }
         if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
             if (lane == 0) { A.out[A.p0 + q] = __longlong_as_double(0x7ff0000000000000LL); A.status[A.p0 + q] = 3; }
             continue;
@@ -264,14 +300,23 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
                 const int supply = lane < nrow ? (rowP >> 8) : ((flip && lane == nrow) ? diff : 0);
                 const int deficit = lane < ncol ? (colP >> 8) : ((!flip && lane == ncol) ? diff : 0);
                 // quantised costs of the residual sub-tile (S6(d)); the dummy row / column costs 0
-                const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+                const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
                 const int cidx = colP & 0xff;
                 const bool rows_doc1 = swap == flip;                             // the rows are doc1's tokens
+                const int32_t *rowtab = nullptr;                                 // GATHER: table rows of the solver's rows / of this lane's column
+                int64_t coloff = 0;
+                if (GATHER) {
+                    const int32_t *r1 = A.rows1 + slot_off(A.s1, tok1, q, a1), *r2 = A.rows2 + slot_off(A.s2, tok2, q, a2);
+                    rowtab = rows_doc1 ? r1 : r2;
+                    coloff = lane < ncol ? (int64_t)__ldg((rows_doc1 ? r2 : r1) + cidx) : 0;
+                }
                 for (int rI = 0; rI < mm; ++rI) {
                     const int ridx = __shfl_sync(kFull, rowP, rI) & 0xff;
                     int ic = 0;
                     if (lane < ncol && rI < nrow) {
-                        const float dv = rows_doc1 ? tile[ridx * u2 + cidx] : tile[cidx * u2 + ridx];
+                        float dv;
+                        if (GATHER) dv = __ldg(A.D + (int64_t)__ldg(rowtab + ridx) * A.V + coloff);       // D is symmetric
+                        else dv = rows_doc1 ? tile[ridx * u2 + cidx] : tile[cidx * u2 + ridx];
                         ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
                     }
                     if (lane < ncc) cost[rI * ldc + lane] = ic;
@@ -281,7 +326,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
             }
         }
         if (lane == 0) {
-            const double maxc_d = (double)A.maxc[q];
+            const double maxc_d = (double)(GATHER ? A.maxc_w[q] : A.maxc[q]);
             const double Cn = __ddiv_rn(1000000.0, maxc_d);       // recomputed: nothing of the set-up stays live across the solver
             double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
             dist = __ddiv_rn(dist, A.pqn[q]);                     // S6(f)
@@ -480,7 +525,7 @@ __device__ long long transport_solve_multi(int m, int nc, int ldc, const int *co
     return warp_sum_ll(tot);
 }
 
-template <int KR, int KC, bool GC>
+template <int KR, int KC, bool GC, bool GATHER>
 __global__ void __launch_bounds__(KR > 2 ? 128 : 256)
 emd_solve_multi_kernel(const __grid_constant__ SolveArgs A)
 {
@@ -499,25 +544,29 @@ emd_solve_multi_kernel(const __grid_constant__ SolveArgs A)
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    const int npairs = A.nlist ? (int)*A.nlist : A.npairs;
 
     for (;;) {
         int q = 0;
         if (lane == 0) q = (int)atomicAdd(A.counter, 1u);
         q = __shfl_sync(kFull, q, 0);
-        if (q >= A.npairs) break;
+        if (q >= npairs) break;
+        if (A.list) q = A.list[q];
         const int meta = A.meta[q];
         if ((meta & 7) != A.cls) continue;
         const int64_t p = A.p0 + q;
-        const float maxc_f = A.maxc[q];
-        if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
-            continue;
-        }
         const int uu = A.u12[q];
         const int u1 = uu & 0xffff, u2 = uu >> 16;
         const bool swap = (meta & kMetaSwap) != 0;
         int64_t a1, a2; int l;
         doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
+        const int32_t *r1 = nullptr, *r2 = nullptr;
+        if (GATHER) { r1 = A.rows1 + slot_off(A.s1, tok1, q, a1); r2 = A.rows2 + slot_off(A.s2, tok2, q, a2); }
+        const float maxc_f = GATHER ? gather_tile_max(A.D, A.V, r1, r2, u1, u2, lane) : A.maxc[q];
+        if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+            continue;
+        }
         const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
         const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
         const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
@@ -556,16 +605,23 @@ emd_solve_multi_kernel(const __grid_constant__ SolveArgs A)
                 deficit[k] = c < n ? pc >> 8 : (c == n ? diff : 0);
             }
             // quantised costs of the residual sub-tile (S6(d)); the dummy column costs 0
-            const float *tile = A.tiles + (int64_t)q * A.tile_stride;
+            const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
+            if (GATHER) {                                        // cj[k] becomes the table row of column k's token
+#pragma unroll
+                for (int k = 0; k < KC; ++k) cj[k] = lane + 32 * k < n ? __ldg((swap ? r1 : r2) + cj[k]) : 0;
+            }
             for (int rI = 0; rI < m; ++rI) {
                 const int i = sridx[rI] & 0xff;
+                const float *drow = GATHER ? A.D + (int64_t)__ldg((swap ? r2 : r1) + i) * A.V : nullptr;      // D is symmetric
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     const int c = lane + 32 * k;
                     if (c < nc) {
                         int ic = 0;
                         if (c < n) {
-                            const float dv = swap ? tile[(int64_t)cj[k] * u2 + i] : tile[(int64_t)i * u2 + cj[k]];
+                            float dv;
+                            if (GATHER) dv = __ldg(drow + cj[k]);
+                            else dv = swap ? tile[(int64_t)cj[k] * u2 + i] : tile[(int64_t)i * u2 + cj[k]];
                             ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
                         }
                         cost[rI * ldc + c] = ic;

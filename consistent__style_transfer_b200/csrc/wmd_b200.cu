@@ -22,6 +22,7 @@
 #include "cost.cuh"
 #include "cost_fast.cuh"
 #include "solve.cuh"
+#include "fused.cuh"
 #include "rwmd.cuh"
 #include "allpairs.cuh"
 #include "emd.cuh"
@@ -73,16 +74,25 @@ struct Workspace {
     DevBuf u12, meta, pqn, extra, maxc;         // per pair
     DevBuf tiles, out, status, scratch, plan, wt1, wt2;
     DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
-    DevBuf counters;                            // 4 x unsigned
+    DevBuf counters;                            // kCounterBytes: work-claim counters, stage / list counts
+    DevBuf biglist;                             // table mode: pairs the fused kernel leaves to the general path
     void release()
     {
         DevBuf *all[] = { &ids1, &ids2, &off1, &off2, &rows1, &cnt1, &ip1, &rows2, &cnt2, &ip2, &u12, &meta, &pqn,
-                          &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &wt1, &wt2, &lb, &l1, &l2, &am1, &am2, &counters };
+                          &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &wt1, &wt2, &lb, &l1, &l2, &am1, &am2, &counters, &biglist };
         for (DevBuf *b : all) b->release();
     }
 };
 
 struct ProfRec { int kind; cudaEvent_t a, b; };
+
+// unsigned slots of Workspace::counters
+constexpr size_t kCounterBytes = 128;
+constexpr int kCtrFused = 4;                    // fused kernel's work-claim counter
+constexpr int kCtrNBig = 5;                     // length of Workspace::biglist
+constexpr int kCtrCost = 8;                     // general cost kernel's claim counter
+constexpr int kCtrStages = 9;                   // planned stages of the fast cost path
+constexpr int kCtrDmax = 12;                    // largest entry of the word-distance table (float bits)
 
 }  // namespace
 
@@ -107,8 +117,12 @@ struct wmd_engine {
     Workspace ws[2];
     // all-pairs mode (allpairs.cuh): V x V distance table (lazy) and a grow-only workspace
     float *dtab = nullptr;
-    bool use_dtab = false;                       // pair path takes its tiles from dtab (wmd_set_distance_table)
+    bool use_dtab = false;                       // pair path takes its costs from dtab (default policy: on when the table fits dtab_budget)
     float dmax = 0.f;
+    size_t dtab_budget = 0;                      // bytes the table may take for the default policy to switch it on
+    double dtab_build_ms = 0.0;                  // wall time of the one-off build
+    int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
+    size_t fused_smem_cached = 0;
     cudaStream_t ap_stream = nullptr;
     DevBuf ap[32];
     unsigned long long *stats = nullptr;        // device [6]
@@ -250,6 +264,8 @@ struct Prof {
     }
 };
 
+bool takes_fused(const wmd_engine *E, bool solve, bool rwmd, int mode);
+
 Vocab make_vocab(const wmd_engine *E)
 {
     Vocab v;
@@ -275,9 +291,9 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
                 const int32_t *u12, float *tiles, int64_t tile_stride, unsigned int *maxc)
 {
     int rc;
-    if ((rc = W.counters.ensure(64))) return rc;
+    if ((rc = W.counters.ensure(kCounterBytes))) return rc;
     if (E->use_dtab && E->dtab) {                        // tiles gathered from the word-distance table
-        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));    // K3's work-claim counters
+        CK(cudaMemsetAsync(W.counters.p, 0, kCounterBytes, st));    // K3's work-claim counters
         CK(cudaMemsetAsync(maxc, 0, (size_t)Bc * 4, st));
         GatherArgs G;
         G.s1 = s1; G.s2 = s2; G.p0 = p0; G.npairs = Bc; G._pad = 0;
@@ -291,7 +307,7 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
     }
     const Vocab vc = make_vocab(E);
     {
-        CK(cudaMemsetAsync(W.counters.p, 0, 64, st));
+        CK(cudaMemsetAsync(W.counters.p, 0, kCounterBytes, st));
         CK(cudaMemsetAsync(maxc, 0, (size_t)Bc * 4, st));
         const int R = E->fast_R, T = kStageTilesMax;
         bool need_general = true;
@@ -300,7 +316,7 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
             PlanArgs P;
             P.s1 = s1; P.s2 = s2; P.p0 = p0; P.npairs = Bc; P.R = R; P.T = T; P._pad = 0;
             P.rows1 = rows1; P.rows2 = rows2; P.u12 = u12;
-            P.stages = W.plan.as<StageRec>(); P.nstages = W.counters.as<unsigned int>() + 9;
+            P.stages = W.plan.as<StageRec>(); P.nstages = W.counters.as<unsigned int>() + kCtrStages;
             const int pblocks = (int)std::min<int64_t>(((int64_t)Bc + 127) / 128, (int64_t)E->sm_count * 16);
             {
                 Prof pr(E, WMD_K_COST, st);
@@ -335,7 +351,7 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
             A.rows1 = rows1; A.rows2 = rows2; A.u12 = u12;
             A.tiles = tiles; A.tile_stride = tile_stride;
             A.maxc = maxc;
-            A.counter = W.counters.as<unsigned int>() + 8;
+            A.counter = W.counters.as<unsigned int>() + kCtrCost;
             const size_t smem = (size_t)kCostWarps * 2 * kUnitRows * A.pitch;
             const int grid = (int)std::min<int64_t>(((int64_t)Bc + kCostWarps - 1) / kCostWarps, (int64_t)E->sm_count * E->cost_ctas_per_sm);
             Prof pr(E, WMD_K_COST, st);
@@ -346,6 +362,129 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
     return WMD_OK;
 }
 
+// K3 launches of one chunk: the class-A / B / C solvers over all pairs of the chunk, or (list mode) over the pairs the
+// fused kernel left behind.  gather: costs come from the word-distance table instead of cost tiles.
+int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2, int64_t p0, int32_t Bc, int ML,
+                   const PairWork &pw, const float *tiles, int64_t tile_stride, const ChunkOut &O, const int32_t *list,
+                   const unsigned int *nlist, bool gather)
+{
+    int rc;
+    for (int cls = kClsA; cls <= kClsC; ++cls) {
+        if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
+        if (cls == kClsC && ML < 64) continue;
+        SolveArgs S;
+        S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
+        const int cap = cls == kClsA ? 32 : (cls == kClsB ? 64 : kMaxDocLen + 1);
+        S.mr = std::min(cap, ML); S.mc = std::min(cap, ML + 1);
+        if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
+        S.ldc = S.mc | 1;
+        S.use_global = cls == kClsC;
+        S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
+        S.tiles = tiles; S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
+        S.counter = W.counters.as<unsigned int>() + cls;
+        S.out = O.out; S.status = O.status;
+        S.list = list; S.nlist = nlist;
+        S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
+        const bool multi = cls != kClsA;
+        int wpb = 8;
+        size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
+                        : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
+                                       : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
+        int blocks_per_sm = E->solve_blocks_per_sm;
+        if (cls == kClsA) { wpb = 4; blocks_per_sm *= 2; }                                // __launch_bounds__(128, 9)
+        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
+        if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
+        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+        const size_t smem = per_warp * wpb;
+        const int ppw = multi ? 1 : 8;                                                    // pairs per warp below which the grid shrinks
+        int grid = (int)std::min<int64_t>(((int64_t)Bc + ppw * wpb - 1) / (ppw * wpb), (int64_t)E->sm_count * blocks_per_sm);
+        grid = std::max(grid, 1);
+        S.scratch = nullptr;
+        if (multi) {
+            // per warp: flow (class B; its costs sit in shared memory), cost + flow (class C)
+            if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
+            S.scratch = W.scratch.as<int32_t>();
+        }
+        Prof pr(E, WMD_K_SOLVE, st);
+#define WMD_LAUNCH_SOLVER(KERNEL)                                                                                        \
+        do {                                                                                                             \
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            KERNEL<<<grid, wpb * 32, smem, st>>>(S);                                                                     \
+        } while (0)
+        if (cls == kClsA) { if (gather) WMD_LAUNCH_SOLVER(emd_solve_small_kernel<true>); else WMD_LAUNCH_SOLVER(emd_solve_small_kernel<false>); }
+        else if (cls == kClsB) {
+            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, false>));
+        } else {
+            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, false>));
+        }
+#undef WMD_LAUNCH_SOLVER
+        CK(cudaGetLastError());
+    }
+    return WMD_OK;
+}
+
+int launch_nbow_pairs(wmd_engine *E, cudaStream_t st, const DocSide &s1, const DocSide &s2, int64_t p0, int32_t Bc, int ML, const PairWork &pw,
+                      const ChunkOut &O, const int32_t *list, const unsigned int *nlist)
+{
+    const int Lp = ML;
+    const int wpb = Lp <= 64 ? 8 : 4;
+    const size_t smem = nbow_smem_per_warp(Lp) * wpb;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((Bc + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+    Prof pr(E, WMD_K_NBOW, st);
+    nbow_pairs_kernel<<<grid, wpb * 32, smem, st>>>(s1, s2, make_vocab(E), p0, Bc, Lp, pw, O.out, O.status, list, nlist);
+    CK(cudaGetLastError());
+    return WMD_OK;
+}
+
+// Table mode (fused.cuh): one persistent warp-per-pair kernel does K1 -> K2 -> K3 for every pair of <= 32 tokens per
+// side; whatever it leaves behind goes through list-mode K1 and the gather-mode solvers.  No cost tiles exist, so the
+// launch geometry does not depend on the longest document of the chunk beyond the per-warp matrix capacity.
+int run_chunk_fused(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2,
+                    int64_t p0, int32_t Bc, int64_t tokcap1, int64_t tokcap2, int ML, const ChunkOut &O)
+{
+    int rc;
+    const bool big = ML >= 32;                           // a pair can only be left behind when a side reaches 32 tokens
+    if ((rc = W.counters.ensure(kCounterBytes)) || (rc = W.biglist.ensure((size_t)Bc * 4))) return rc;
+    CK(cudaMemsetAsync(W.counters.p, 0, kCounterBytes, st));
+    FusedArgs F;
+    F.s1 = s1; F.s2 = s2; F.vc = make_vocab(E); F.D = E->dtab; F.p0 = p0; F.npairs = Bc;
+    F.cap = std::min(32, ML + 1); F.ldc = F.cap | 1; F._pad = 0;
+    F.counter = W.counters.as<unsigned int>() + kCtrFused;
+    F.biglist = W.biglist.as<int32_t>(); F.nbig = W.counters.as<unsigned int>() + kCtrNBig;
+    F.stats = E->stats; F.out = O.out; F.status = O.status;
+    {
+        const int wpb = 4;
+        const size_t smem = fused_smem_per_warp(F.cap, F.ldc) * wpb;
+        if (smem != E->fused_smem_cached) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(wmd_fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wmd_fused_small_kernel, wpb * 32, smem));
+            if (nb < 1) return fail(WMD_ECUDA, "wmd_fused_small_kernel cannot be resident");
+            E->fused_blocks_per_sm = nb; E->fused_smem_cached = smem;
+        }
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * E->fused_blocks_per_sm));
+        Prof pr(E, WMD_K_FUSED, st);
+        wmd_fused_small_kernel<<<grid, wpb * 32, smem, st>>>(F);
+        CK(cudaGetLastError());
+    }
+    if (!big) return WMD_OK;
+    if ((rc = W.rows1.ensure(tokcap1 * 4)) || (rc = W.cnt1.ensure(tokcap1 * 4)) || (rc = W.ip1.ensure(tokcap1 * 4)) ||
+        (rc = W.rows2.ensure(tokcap2 * 4)) || (rc = W.cnt2.ensure(tokcap2 * 4)) || (rc = W.ip2.ensure(tokcap2 * 4)) ||
+        (rc = W.u12.ensure((size_t)Bc * 4)) || (rc = W.meta.ensure((size_t)Bc * 4)) || (rc = W.pqn.ensure((size_t)Bc * 8)) ||
+        (rc = W.extra.ensure((size_t)Bc * 8)) || (rc = W.maxc.ensure((size_t)Bc * 4)))
+        return rc;
+    PairWork pw;
+    pw.rows1 = W.rows1.as<int32_t>(); pw.cnt1 = W.cnt1.as<int32_t>(); pw.ip1 = W.ip1.as<int32_t>();
+    pw.rows2 = W.rows2.as<int32_t>(); pw.cnt2 = W.cnt2.as<int32_t>(); pw.ip2 = W.ip2.as<int32_t>();
+    pw.u12 = W.u12.as<int32_t>(); pw.meta = W.meta.as<int32_t>(); pw.pqn = W.pqn.as<double>(); pw.extra = W.extra.as<double>();
+    pw.stats = E->stats; pw.exact = 0; pw._pad = 0; pw.wt1 = nullptr; pw.wt2 = nullptr;
+    const int32_t *list = W.biglist.as<int32_t>();
+    const unsigned int *nlist = W.counters.as<unsigned int>() + kCtrNBig;
+    if ((rc = launch_nbow_pairs(E, st, s1, s2, p0, Bc, ML, pw, O, list, nlist))) return rc;
+    return launch_solvers(E, W, st, s1, s2, p0, Bc, ML, pw, nullptr, 0, O, list, nlist, true);
+}
+
 // Launch K1..K3 for pairs [p0, p0 + Bc) on stream st. tok caps bound the token slots of the chunk.
 int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2,
               int64_t p0, int32_t Bc, int64_t tokcap1, int64_t tokcap2, int32_t ml1, int32_t ml2,
@@ -354,13 +493,15 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
     if (Bc <= 0) return WMD_OK;
     ml1 = std::max(ml1, 1); ml2 = std::max(ml2, 1);
     const int ML = std::max(ml1, ml2);
+    if (takes_fused(E, O.solve, O.rwmd, O.mode))
+        return run_chunk_fused(E, W, st, s1, s2, p0, Bc, tokcap1, tokcap2, ML, O);
     const int64_t tile_stride = (int64_t)ml1 * ml2;
     int rc;
     if ((rc = W.rows1.ensure(tokcap1 * 4)) || (rc = W.cnt1.ensure(tokcap1 * 4)) || (rc = W.ip1.ensure(tokcap1 * 4)) ||
         (rc = W.rows2.ensure(tokcap2 * 4)) || (rc = W.cnt2.ensure(tokcap2 * 4)) || (rc = W.ip2.ensure(tokcap2 * 4)) ||
         (rc = W.u12.ensure((size_t)Bc * 4)) || (rc = W.meta.ensure((size_t)Bc * 4)) || (rc = W.pqn.ensure((size_t)Bc * 8)) ||
         (rc = W.extra.ensure((size_t)Bc * 8)) || (rc = W.maxc.ensure((size_t)Bc * 4)) ||
-        (rc = W.tiles.ensure((size_t)Bc * tile_stride * 4)) || (rc = W.counters.ensure(64)))
+        (rc = W.tiles.ensure((size_t)Bc * tile_stride * 4)) || (rc = W.counters.ensure(kCounterBytes)))
         return rc;
 
     // ---- K1
@@ -374,17 +515,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         if ((rc = W.wt1.ensure((size_t)tokcap1 * 8)) || (rc = W.wt2.ensure((size_t)tokcap2 * 8))) return rc;
         pw.wt1 = W.wt1.as<double>(); pw.wt2 = W.wt2.as<double>();
     }
-    const Vocab vc = make_vocab(E);
-    {
-        const int Lp = ML;
-        const int wpb = Lp <= 64 ? 8 : 4;
-        const size_t smem = nbow_smem_per_warp(Lp) * wpb;
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::min<int64_t>((Bc + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
-        Prof pr(E, WMD_K_NBOW, st);
-        nbow_pairs_kernel<<<grid, wpb * 32, smem, st>>>(s1, s2, vc, p0, Bc, Lp, pw, O.out, O.status);
-        CK(cudaGetLastError());
-    }
+    if ((rc = launch_nbow_pairs(E, st, s1, s2, p0, Bc, ML, pw, O, nullptr, nullptr))) return rc;
     // ---- K2
     if ((rc = launch_cost(E, W, st, s1, s2, p0, Bc, ml1, ml2, tokcap1, tokcap2, pw.rows1, pw.rows2, pw.u12, W.tiles.as<float>(), tile_stride,
                           W.maxc.as<unsigned int>())))
@@ -426,58 +557,20 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         CK(cudaGetLastError());
         return WMD_OK;
     }
-    for (int cls = kClsA; cls <= kClsC; ++cls) {
-        if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
-        if (cls == kClsC && ML < 64) continue;
-        SolveArgs S;
-        S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
-        const int cap = cls == kClsA ? 32 : (cls == kClsB ? 64 : kMaxDocLen + 1);
-        S.mr = std::min(cap, ML); S.mc = std::min(cap, ML + 1);
-        if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
-        S.ldc = S.mc | 1;
-        S.use_global = cls == kClsC;
-        S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
-        S.tiles = W.tiles.as<float>(); S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
-        S.counter = W.counters.as<unsigned int>() + cls;
-        S.out = O.out; S.status = O.status;
-        const bool multi = cls != kClsA;
-        int wpb = 8;
-        size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
-                        : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
-                                       : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
-        int blocks_per_sm = E->solve_blocks_per_sm;
-        if (cls == kClsA) { wpb = 4; blocks_per_sm *= 2; }                                // __launch_bounds__(128, 9)
-        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
-        if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
-        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
-        const size_t smem = per_warp * wpb;
-        const int ppw = multi ? 1 : 8;                                                    // pairs per warp below which the grid shrinks
-        int grid = (int)std::min<int64_t>(((int64_t)Bc + ppw * wpb - 1) / (ppw * wpb), (int64_t)E->sm_count * blocks_per_sm);
-        grid = std::max(grid, 1);
-        S.scratch = nullptr;
-        if (multi) {
-            // per warp: flow (class B; its costs sit in shared memory), cost + flow (class C)
-            if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
-            S.scratch = W.scratch.as<int32_t>();
-        }
-        Prof pr(E, WMD_K_SOLVE, st);
-        if (cls == kClsA) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_small_kernel<<<grid, wpb * 32, smem, st>>>(S);
-        } else if (cls == kClsB) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_multi_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_multi_kernel<2, 2, false><<<grid, wpb * 32, smem, st>>>(S);
-        } else {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_multi_kernel<8, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emd_solve_multi_kernel<8, 9, true><<<grid, wpb * 32, smem, st>>>(S);
-        }
-        CK(cudaGetLastError());
-    }
-    return WMD_OK;
+    return launch_solvers(E, W, st, s1, s2, p0, Bc, ML, pw, W.tiles.as<float>(), tile_stride, O, nullptr, nullptr, false);
 }
 
-int64_t chunk_pairs(int ml1, int ml2)
+int ensure_dtab(wmd_engine *E, cudaStream_t st);
+
+// a job of this kind runs on the fused table-mode path (run_chunk_fused): no cost tiles, no per-length chunk limit
+bool takes_fused(const wmd_engine *E, bool solve, bool rwmd, int mode)
 {
+    return E->use_dtab && E->dtab && solve && !rwmd && mode == WMD_MODE_PYEMD;
+}
+
+int64_t chunk_pairs(int ml1, int ml2, bool fused)
+{
+    if (fused) return 65536;
     const int64_t tile = (int64_t)std::max(ml1, 1) * std::max(ml2, 1) * 4;
     int64_t c = (int64_t)(768ll << 20) / tile;
     c = std::min<int64_t>(c, 65536);
@@ -531,6 +624,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
     if (J.npairs < 0 || (J.npairs > 0 && (!J.off1 || !J.off2))) return fail(WMD_EINVAL, "null offsets");
     if (J.npairs == 0) return WMD_OK;
     if ((J.off1[J.npairs] > J.off1[0] && !J.ids1) || (J.off2[J.npairs] > J.off2[0] && !J.ids2)) return fail(WMD_EINVAL, "null ids");
+    if (E->use_dtab && !E->dtab && (rc = ensure_dtab(E, E->streams[0]))) return rc;      // first call: build the word-distance table
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_fork, E->streams[0]));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
@@ -545,7 +639,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
             cudaStreamSynchronize(E->streams[0]); cudaStreamSynchronize(E->streams[1]);
             return rc;
         }
-        const int32_t Bc = (int32_t)std::min<int64_t>(Btry, chunk_pairs(ml1, ml2));   // a shorter prefix keeps the same bounds
+        const int32_t Bc = (int32_t)std::min<int64_t>(Btry, chunk_pairs(ml1, ml2, takes_fused(E, J.solve, J.rwmd, J.mode)));   // a shorter prefix keeps the same bounds
         Bnext = Bc;
         Workspace &W = E->ws[slot];
         cudaStream_t st = E->streams[slot];
@@ -608,13 +702,14 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     if (ml1 < 0 || ml2 < 0 || ml1 > WMD_MAX_DOC_LEN || ml2 > WMD_MAX_DOC_LEN)
         return fail(WMD_EINVAL, "max_len must be within [0, %d]", WMD_MAX_DOC_LEN);
     ml1 = std::max(ml1, 1); ml2 = std::max(ml2, 1);
+    if (E->use_dtab && !E->dtab && (rc = ensure_dtab(E, E->streams[0]))) return rc;      // first call only (host-synchronous once)
     CK(cudaEventRecord(E->ev_fork, us));
     CK(cudaStreamWaitEvent(E->streams[0], E->ev_fork, 0));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_join[0], 0));        // stats reset precedes both streams' kernels
-    const int64_t CH = chunk_pairs(ml1, ml2);
+    const int64_t CH = chunk_pairs(ml1, ml2, takes_fused(E, true, false, mode));
     int slot = 0;
     for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot = (slot ^ 1) & E->slot_mask) {
         const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - c0);
@@ -654,6 +749,10 @@ int ensure_dtab(wmd_engine *E, cudaStream_t st)
 {
     if (E->dtab) return WMD_OK;
     int rc;
+    // one-off and host-synchronous: the build borrows the slot-0 workspace, so nothing of an earlier asynchronous
+    // device call may still be in flight on it
+    CK(cudaDeviceSynchronize());
+    const auto t_build0 = std::chrono::steady_clock::now();
     const int64_t V = E->V;
     const size_t bytes = (size_t)V * V * 4;
     size_t freeb = 0, totalb = 0;
@@ -688,7 +787,7 @@ int ensure_dtab(wmd_engine *E, cudaStream_t st)
         if (cudaGetLastError() != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "dtab_scatter_kernel launch failed"); }
     }
     // largest distance in the table: scales the pruning margin (allpairs.cuh)
-    unsigned int *dmaxbits = W.counters.as<unsigned int>() + 12;
+    unsigned int *dmaxbits = W.counters.as<unsigned int>() + kCtrDmax;
     if (cudaMemsetAsync(dmaxbits, 0, 4, st) != cudaSuccess) { cudaFree(D); return fail(WMD_ECUDA, "memset failed"); }
     table_max_kernel<<<E->sm_count * 4, 256, 0, st>>>(D, (int64_t)V * V, dmaxbits);
     unsigned int hb = 0;
@@ -698,6 +797,7 @@ int ensure_dtab(wmd_engine *E, cudaStream_t st)
     }
     memcpy(&E->dmax, &hb, 4);
     E->dtab = D;
+    E->dtab_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
     return WMD_OK;
 }
 
@@ -938,12 +1038,16 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         normalize_rows_kernel<<<(unsigned)((V + 127) / 128), 128>>>(E->table, V, d, E->ld, E->plan);
         if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(WMD_ECUDA, "normalize failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
-    if (const char *v = getenv("WMD_DTAB")) {             // WMD_DTAB=1: pair entries gather their tiles from the V x V table
-        if (atoi(v)) {
-            int rc;
-            if ((rc = ensure_dtab(E, E->streams[0]))) return bail(rc);
-            E->use_dtab = true;
-        }
+    // Default policy of the pair entries: keep the V x V word-distance table when it fits the budget (built by the
+    // first scoring call, so a handle that never scores never pays for it).  WMD_DTAB=0 / 1 forces the direct path /
+    // the table; WMD_DTAB_BUDGET_MB moves the budget (default 4 GiB and at most a quarter of the free device memory).
+    {
+        size_t freeb = 0, totalb = 0;
+        cudaMemGetInfo(&freeb, &totalb);
+        E->dtab_budget = std::min<size_t>((size_t)4 << 30, freeb / 4);
+        if (const char *v = getenv("WMD_DTAB_BUDGET_MB")) E->dtab_budget = (size_t)std::max(0, atoi(v)) << 20;
+        E->use_dtab = (size_t)V * (size_t)V * 4 <= E->dtab_budget;
+        if (const char *v = getenv("WMD_DTAB")) E->use_dtab = atoi(v) != 0;
     }
     *out = E;
     return WMD_OK;
@@ -1181,6 +1285,16 @@ int wmd_set_distance_table(wmd_handle E, int32_t enabled)
     if ((rc = set_device(E))) return rc;
     if ((rc = ensure_dtab(E, E->streams[0]))) return rc;
     E->use_dtab = true;
+    return WMD_OK;
+}
+
+int wmd_distance_table_info(wmd_handle E, int64_t *bytes, double *build_ms, int32_t *enabled, int32_t *resident)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (bytes) *bytes = (int64_t)E->V * E->V * 4;
+    if (build_ms) *build_ms = E->dtab_build_ms;
+    if (enabled) *enabled = E->use_dtab ? 1 : 0;
+    if (resident) *resident = E->dtab ? 1 : 0;
     return WMD_OK;
 }
 

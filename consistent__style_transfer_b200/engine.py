@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from ._lib import c_f32p, c_f64p, c_i32p, c_i64p
 
-KERNEL_KINDS = ("nbow", "cost", "solve", "rwmd", "misc")
+KERNEL_KINDS = ("nbow", "cost", "solve", "rwmd", "misc", "fused")
 MODE_PYEMD = 0      # the reference's value: pyemd's 1e6-grid integer optimum (bit-faithful)
 MODE_EXACT = 1      # additive: the real-valued transportation optimum in FP64
 _MODES = {"pyemd": MODE_PYEMD, "exact": MODE_EXACT, MODE_PYEMD: MODE_PYEMD, MODE_EXACT: MODE_EXACT}
@@ -41,7 +41,10 @@ class WMDEngine:
     """One handle = one device copy of the embedding table + maps + workspace."""
 
     def __init__(self, vectors: np.ndarray, normalize: bool = False, device: int = 0,
-                 rank: Optional[np.ndarray] = None, token_map: Optional[np.ndarray] = None):
+                 rank: Optional[np.ndarray] = None, token_map: Optional[np.ndarray] = None,
+                 distance_table: Optional[bool] = None):
+        """distance_table: None = the library's policy (word-distance table when V * V * 4 bytes fit its budget),
+        True / False = force the table / the direct path (``set_distance_table``)."""
         self._L = _lib.load()
         vectors = np.asarray(vectors)
         if vectors.ndim != 2:
@@ -57,6 +60,8 @@ class WMDEngine:
             self.set_rank(rank)
         if token_map is not None:
             self.set_token_map(token_map)
+        if distance_table is not None:
+            self.set_distance_table(bool(distance_table))
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -247,9 +252,16 @@ class WMDEngine:
         _lib.check(self._L.wmd_set_serial(self._handle(), int(bool(enabled))))
 
     def set_distance_table(self, enabled: bool = True):
-        """Build (once) the V x V float32 word-distance table and let the pair entries gather their cost tiles
-        from it instead of recomputing them (V * V * 4 bytes of device memory; results are bit-identical)."""
+        """True: build (once) the V x V float32 word-distance table now and let the pair entries take their costs
+        from it (the default whenever the table fits the library's budget; then the first scoring call builds it).
+        False: the direct path that recomputes every distance from the embedding rows.  Results are bit-identical."""
         _lib.check(self._L.wmd_set_distance_table(self._handle(), int(bool(enabled))))
+
+    def distance_table_info(self):
+        b = ctypes.c_int64(); ms = ctypes.c_double(); en = ctypes.c_int32(); res = ctypes.c_int32()
+        _lib.check(self._L.wmd_distance_table_info(self._handle(), ctypes.byref(b), ctypes.byref(ms), ctypes.byref(en),
+                                                   ctypes.byref(res)))
+        return {"bytes": int(b.value), "build_ms": float(ms.value), "enabled": bool(en.value), "resident": bool(res.value)}
 
     def profile(self, reset: bool = True):
         ms = (ctypes.c_double * len(KERNEL_KINDS))()

@@ -146,14 +146,21 @@ int wmd_allpairs_topk_host(wmd_handle h, const int32_t *idsA, const int64_t *off
                            int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist,
                            int64_t *stats, double *ms);
 
-/* Optional word-distance table for the pair entries (additive; the reference has no counterpart: gensim's
- * wmdistance, models/keyedvectors.py [gensim 3.8], recomputes every word distance per call, as the default path
- * here does).  enabled != 0 builds, once per handle, the float32 distance of every two rows of the embedding
- * table -- V * V * 4 bytes of device memory, computed by the pair path's own cost kernels, so each entry is
- * bit-identical to what they produce for a pair -- and lets every later pair call gather its cost tiles from it
- * instead of recomputing them.  Results do not change.  WMD_ENOMEM when the table does not fit.  The all-pairs
- * entry builds and uses the same table on its own.  enabled == 0 returns to the direct path (the table is kept). */
+/* Word-distance table of the pair entries (the reference has no counterpart: gensim's wmdistance,
+ * models/keyedvectors.py [gensim 3.8], recomputes every word distance on every call).  A handle keeps the float32
+ * distance of every two rows of its embedding table -- V * V * 4 bytes of device memory, computed ONCE by the pair
+ * path's own cost kernels, so each entry is bit-identical to what they produce for a pair -- and every pair call
+ * takes its costs from it: one fused kernel per chunk does nBOW, cost gather and the exact solve of a pair in one
+ * warp (csrc/fused.cuh), nothing in between touches device memory.  Results do not change.
+ * Default policy: ON when the table fits the budget (4 GiB and at most a quarter of the free device memory;
+ * environment WMD_DTAB_BUDGET_MB, WMD_DTAB=0/1), built by the first scoring call of the handle (that call is
+ * host-synchronous once, also through a *_dev entry).  enabled != 0 forces it on and builds it now (WMD_ENOMEM
+ * when it does not fit); enabled == 0 returns to the direct path that recomputes every distance from the embedding
+ * rows (the table, if built, is kept).  The all-pairs entry builds and uses the same table on its own. */
 int wmd_set_distance_table(wmd_handle h, int32_t enabled);
+/* bytes the table takes (V * V * 4), wall milliseconds its one-off build took (0 until built), whether the pair
+ * entries use it, whether it is resident.  Any pointer may be NULL. */
+int wmd_distance_table_info(wmd_handle h, int64_t *bytes, double *build_ms, int32_t *enabled, int32_t *resident);
 
 /* instrumentation ----------------------------------------------------------------------------- */
 
@@ -167,7 +174,8 @@ int wmd_set_serial(wmd_handle h, int32_t enabled);
 #define WMD_K_SOLVE  2
 #define WMD_K_RWMD   3
 #define WMD_K_MISC   4
-#define WMD_K_COUNT  5
+#define WMD_K_FUSED  5   /* table mode: nBOW + cost gather + solve of one pair in one warp (fused.cuh) */
+#define WMD_K_COUNT  6
 /* accumulated since the last reset: ms[k] device milliseconds, launches[k] launch count */
 int wmd_get_profile(wmd_handle h, double *ms, int64_t *launches, int32_t reset);
 /* totals of the last wmd_pairs_* call: sum over pairs of tokens, unique rows and tile cells

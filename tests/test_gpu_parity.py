@@ -21,6 +21,13 @@ def eng_mod():
     return engine
 
 
+@pytest.fixture(params=[True, False], ids=["table", "direct"])
+def dtab(request):
+    """Both cost sources of the pair entries: the word-distance table with its fused warp-per-pair kernel (the
+    default policy) and the direct path that recomputes every distance from the embedding rows."""
+    return request.param
+
+
 def _assert_wmd_equal(got, st, want, wst, rtol=1e-12):
     assert np.array_equal(st, wst), np.nonzero(st != wst)[0][:10]
     fin = np.isfinite(want)
@@ -68,20 +75,20 @@ def test_nbow_bit_exact(eng_mod, oracle, use_rank):
     (256, "yelp", "independent", 800), (512, "yelp", "independent", 800), (1000, "yelp", "noised", 300),
     (200, "book", "independent", 400),
 ])
-def test_wmd_pairs_match_oracle(eng_mod, oracle, d, shape, variant, B):
+def test_wmd_pairs_match_oracle(eng_mod, oracle, d, shape, variant, B, dtab):
     V = 2000
     table = workload.make_table(V, d, seed=2)
     ids1, off1, ids2, off2 = workload.make_pairs(B, shape, variant, V=V, seed=7)
     rng = np.random.default_rng(5)
     ids1 = ids1.copy(); ids1[rng.random(len(ids1)) < 0.03] = -1      # OOV tokens
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
     _assert_wmd_equal(got, st, want, wst)
     e.close()
 
 
-def test_wmd_pairs_with_rank_and_token_map(eng_mod, oracle):
+def test_wmd_pairs_with_rank_and_token_map(eng_mod, oracle, dtab):
     V = 800
     rng = np.random.default_rng(12)
     table = workload.make_table(V, 100, seed=3)
@@ -90,20 +97,20 @@ def test_wmd_pairs_with_rank_and_token_map(eng_mod, oracle):
     tmap = np.full(ntok, -1, np.int32)
     tmap[rng.permutation(ntok)[:V]] = np.arange(V, dtype=np.int32)
     t1, off1, t2, off2 = workload.make_pairs(1500, "yelp", "noised", V=ntok, seed=9)
-    e = eng_mod.WMDEngine(table, rank=rank, token_map=tmap)
+    e = eng_mod.WMDEngine(table, rank=rank, token_map=tmap, distance_table=dtab)
     got, st = e.wmd_pairs(t1, off1, t2, off2)
     want, wst = oracle.batch_wmd(table, tmap[t1], off1, tmap[t2], off2, rank=rank, nthreads=8)
     _assert_wmd_equal(got, st, want, wst)
     e.close()
 
 
-def test_early_outs_and_edge_cases(eng_mod, oracle):
+def test_early_outs_and_edge_cases(eng_mod, oracle, dtab):
     table = workload.make_table(50, 16, seed=3)
     table[7] = table[6]
     docs1 = [[-1], [1], [1, 1], [6], [1, 2], [], [3], [5, 5, 5, 9], [99999]]
     docs2 = [[1], [], [1], [7], [2, 1], [], [9], [9, 5], [1]]
     ids1, off1 = workload.to_csr(docs1); ids2, off2 = workload.to_csr(docs2)
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, np.where(ids1 >= 50, -1, ids1).astype(np.int32), off1, ids2, off2)
     assert list(st) == [1, 1, 2, 3, 0, 1, 0, 0, 1]
@@ -121,12 +128,12 @@ def test_early_outs_and_edge_cases(eng_mod, oracle):
 
 
 @pytest.mark.parametrize("L", [8, 33, 64, 128, 256])
-def test_length_sweep_matches_oracle(eng_mod, oracle, L):
+def test_length_sweep_matches_oracle(eng_mod, oracle, L, dtab):
     V = 10000
     table = workload.make_table(V, 300, seed=0)
     B = 96 if L >= 128 else 400
     ids1, off1, ids2, off2 = workload.make_pairs(B, f"fixed:{L}", "independent", V=V, seed=L)
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
     _assert_wmd_equal(got, st, want, wst)
@@ -139,11 +146,13 @@ def test_length_sweep_matches_oracle(eng_mod, oracle, L):
     ("uniform:1-90", "independent", 3000, 300, 1500), ("uniform:1-256", "independent", 400, 64, 600), ("fixed:256", "independent", 300, 8, 200),
     ("uniform:30-70", "noised", 150, 100, 800), ("fixed:100", "independent", 120, 32, 500),
     ("fixed:200", "noised", 5000, 16, 300), ("uniform:40-45", "independent", 10000, 300, 1000),
+    # around the fused kernel's limits: 32-token documents whose residual problem needs 33 columns, documents either side of 32 tokens
+    ("uniform:28-36", "independent", 10000, 64, 1500), ("fixed:32", "independent", 10000, 32, 600), ("uniform:30-33", "noised", 4000, 100, 900),
 ])
-def test_mixed_long_documents_match_oracle(eng_mod, oracle, shape, variant, V, d, B):
+def test_mixed_long_documents_match_oracle(eng_mod, oracle, shape, variant, V, d, B, dtab):
     table = workload.make_table(V, d, seed=11)
     ids1, off1, ids2, off2 = workload.make_pairs(B, shape, variant, V=V, seed=13)
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
     _assert_wmd_equal(got, st, want, wst)
@@ -162,7 +171,7 @@ def _chain_table(n, eps=0.002, h=0.2, d=8):
 
 
 @pytest.mark.parametrize("n", [12, 31, 33, 64, 100, 200, 256])
-def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n):
+def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n, dtab):
     # paths longer than 32 hops are walked in pieces by the class B / C solver (solve.cuh: transport_solve_multi)
     table = _chain_table(n)
     fwd = (np.arange(1, n + 1), n + 1 + np.arange(0, n))
@@ -176,7 +185,7 @@ def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n):
         docs1.append(a.astype(np.int32)); docs2.append(b.astype(np.int32))
     ids1, off1 = workload.to_csr(docs1)
     ids2, off2 = workload.to_csr(docs2)
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=4)
     _assert_wmd_equal(got, st, want, wst)
@@ -196,9 +205,11 @@ def test_distance_table_path_is_bit_identical(eng_mod, oracle, shape, variant, V
     rng = np.random.default_rng(3)
     ids2 = ids2.copy(); ids2[rng.random(len(ids2)) < 0.02] = -1
     rk = rng.permutation(V).astype(np.int32) if rank else None
-    e = eng_mod.WMDEngine(table, rank=rk)
+    e = eng_mod.WMDEngine(table, rank=rk, distance_table=False)
+    assert not e.distance_table_info()["resident"]
     direct, st0 = e.wmd_pairs(ids1, off1, ids2, off2)
     e.set_distance_table(True)
+    assert e.distance_table_info()["resident"]
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     lb_t = e.rwmd_pairs(ids1, off1, ids2, off2)
     e.set_distance_table(False)
@@ -230,13 +241,13 @@ def test_rwmd_matches_oracle(eng_mod, oracle):
     e.close()
 
 
-def test_device_entries_match_host_entry(eng_mod):
+def test_device_entries_match_host_entry(eng_mod, dtab):
     import torch
     V = 3000
     table = workload.make_table(V, 300, seed=8)
     B = 70000                                                      # > one chunk: exercises both streams
     ids1, off1, ids2, off2 = workload.make_pairs(B, "yelp", "independent", V=V, seed=21)
-    e = eng_mod.WMDEngine(table)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
     host, hst = e.wmd_pairs(ids1, off1, ids2, off2)
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(a).to(dev)
