@@ -4,20 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's B200 engine
     python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (oracle port)
 
-A "step" is one pass of the hot path (nBOW -> gather -> cost tile -> exact EMD) over one batch of
-synthetic pairs: 1 M Yelp-shape pairs per GPU (len 1..20, d=300, V=10k, `independent` variant =
-worst case).  Weak scaling: every rank scores its own 1 M pairs; nothing but the
-final float64 scores crosses NCCL (one all-gather per step, inside the timed region; pairs are
-independent -- BASELINE north_star / SURVEY 8(e)).
+A "step" is one pass of the hot path (nBOW -> word distances -> exact EMD) over one batch of synthetic pairs:
+1 M Yelp-shape pairs per GPU (len 1..20, d=300, V=10k, `independent` variant = worst case).
+Weak scaling: the global batch holds N x 1 M pairs, `sharding.partition_by_tokens` deals every rank a contiguous
+slice of equal token count, and nothing but the final scores crosses NCCL (`sharding.gather_scores`, inside the timed
+region; pairs are independent -- BASELINE north_star / SURVEY 8(e)).
 
-value  = pairs/s with ids/offsets already resident in HBM (wmd_pairs_dev), CUDA-event timed.
-e2e    = pairs/s through the host entry wmd_pairs_host on PINNED HOST buffers: H2D of ids+offsets and
-         D2H of scores+status are inside the timed region of every step.
-roofline.achieved = algorithmic bytes of the step (4(n1+n2) + 4d(u1+u2) + 8 per pair,
-         summed from the engine's own counters) / the dominant kernel's summed launch time in the
-         step, from CUDA events recorded on the kernels' own streams during the timed steps.
-cpu_baseline / --impl reference = oracle/wmd_oracle.py's gensim-shaped python loop + C emd_hat
-         (the reference itself cannot be installed: gensim and pyemd are absent).
+value  = pairs/s with the rank's slice already resident in HBM (wmd_pairs_dev), CUDA-event timed, max over ranks.
+e2e    = pairs/s through the public call on HOST buffers: N = 1 `WMDEngine.wmd_pairs` (wmd_pairs_host) on pinned
+         arrays, N > 1 `sharding.wmd_pairs_sharded(engine.wmd_pairs_torch, ...)` on the global batch + a device->host
+         read of the gathered scores; H2D of ids + offsets and D2H of scores + status inside the timed region.
+The engine runs its default policy: the V x V word-distance table (400 MB at V = 10k) is built ONCE by the first call
+(warm-up; `table_build_ms`, `table_break_even_pairs`) and every step takes its costs from it through the fused
+warp-per-pair kernel; `without_table` is the same measurement on the direct path that recomputes every float32
+distance from the embedding rows, as gensim does.  Both produce identical bits.
+roofline = the dominant kernel against the HBM roofline with SURVEY 8(d)'s algorithmic bytes (the contract's
+         convention), next to what actually binds it: instruction issue (`issue`, `binding`), from the ncu capture of
+         the same kernel kept under profiles/ (`traffic_source` names file and commit).
+cpu_baseline / --impl reference = oracle/wmd_oracle.py's gensim-shaped python loop + C emd_hat (the reference itself
+         cannot be installed: gensim and pyemd are absent).
+Sub-records of the default run (one JSON line): `allpairs` (configs[3], strong scaling), `sweep` (configs[4] plus a
+mixed-length workload), `latency` (configs[2]: one collate batch through the reference's own call surface; N = 1).
 """
 from __future__ import annotations
 
@@ -40,12 +47,7 @@ from consistent__style_transfer_b200 import workload  # noqa: E402
 
 METRIC = "wmd_sentence_pairs_per_sec"
 UNIT = "pairs/s"
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (one chunk of 65 536 Yelp-shape pairs) from the
-# `ncu --set full` capture summarised in profiles/r01_final_ncu_all_kernels.txt: the table is L2-resident, so
-# DRAM only sees ids, plan records, tiles and scores.
-NCU_DRAM_BYTES_PER_LAUNCH = {"cost": 41.32e6 + 2.95e6, "solve": 38.40e6 + 0.05e6, "nbow": 6.62e6 + 0.52e6}
-NCU_SOURCE = "profiles/r01_final_ncu_all_kernels.txt (262 144-pair run, chunk of 65 536 pairs per launch)"
+NCU_FILE = os.path.join(ROOT, "profiles", "r02_ncu_fused.json")     # written by tools/ncu_summary.py from the .ncu-rep
 
 
 def parse_args():
@@ -61,9 +63,11 @@ def parse_args():
     ap.add_argument("--vocab", type=int, default=10_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-table-arm", action="store_true", help="skip the additional word-distance-table measurement")
+    ap.add_argument("--no-direct-arm", action="store_true", help="skip the additional measurement without the word-distance table")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no allpairs / sweep / latency sub-records")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "allpairs", "latency", "sweep"],
-                    help="pairs = BASELINE configs[1] (the driver's headline); allpairs = configs[3], top-k with RWMD pruning")
+                    help="pairs = BASELINE configs[1] (the driver's headline, with the other modes as sub-records); "
+                         "allpairs / sweep / latency = that mode alone")
     ap.add_argument("--lengths", default="8,16,32,64,128,256", help="sweep: document lengths")
     ap.add_argument("--docs", type=int, default=100_000, help="allpairs: documents in the set (self join)")
     ap.add_argument("--topk", type=int, default=16)
@@ -73,6 +77,15 @@ def parse_args():
 
 def workload_name(a):
     return f"{a.shape}-shape {a.variant} pairs, len<=20, d={a.d}, V={a.vocab}, {a.pairs} pairs/GPU/step"
+
+
+def config_dict(a, n_gpus):
+    """The same dictionary in both arms (the reference arm times a bounded sample of this workload per step)."""
+    return {"workload": workload_name(a), "pairs_per_gpu": a.pairs, "global_pairs": n_gpus * a.pairs,
+            "cost": "float32 numpy-order (bit-exact)", "emd": "pyemd 1e6-grid integer optimum, exact",
+            "l2": "256 MiB flush write between timed steps",
+            "parallelism": f"pairs sharded over {n_gpus} GPU(s) in token-balanced contiguous slices; no data-path "
+                           f"collective, one NCCL gather of the float64 scores + status per step inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,10 +147,20 @@ def cpu_c_port(table, pairs, n_sample, cores):
     return n / (time.perf_counter() - t0)
 
 
+def cpu_one_core(table, pairs, n_sample):
+    """The reference's real configuration: one process, one thread (src/main_pretrain.py:120-122, num_workers unset)."""
+    _cpu_init(table, *pairs)
+    _cpu_worker((0, 8))
+    dt, n, _ = _cpu_worker((0, n_sample))
+    return n / dt
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(a.gpus, world)
     cores = os.cpu_count() or 1
     table = workload.make_table(a.vocab, a.d, seed=0)
     per_step = a.cpu_sample or 1000 * cores
@@ -152,11 +175,15 @@ def run_reference(a):
     total = sum(times)
     value = per_step * a.steps / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample_pairs_per_step": per_step,
-                   "note": "reference cannot be installed (gensim/pyemd absent); oracle port of its CPU path"},
+        "config": config_dict(a, n_gpus),
+        "arm": {"sample_pairs_per_step": per_step,
+                "note": "the reference cannot be installed (gensim / pyemd absent): this is the oracle port of its CPU path, "
+                        "timed on a bounded sample of the configured workload per step and reported as a rate; "
+                        "liboracle_wmd.so (the C emd_hat) is loaded inside the forked pool workers, so a hook that lists "
+                        "the shared objects of THIS process does not see it"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} pairs/step of the same workload, python per-pair loop + C emd_hat, "
                                    f"{cores} worker processes, wall time per step"},
@@ -209,451 +236,519 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_b200(a):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state shared by the arms: ranks, device, process group, table, engine."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    n_gpus = max(a.gpus, world)
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        self.a = a
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.n_gpus = max(a.gpus, self.world)
+        self.table = None
+        self.eng = None
+        self.dev = None
+        self.flush = None
 
-    table = workload.make_table(a.vocab, a.d, seed=0)
-    pairs = workload.make_pairs(a.pairs, a.shape, a.variant, V=a.vocab, seed=1 + rank)
-    ids1, off1, ids2, off2 = pairs
-    ml1, ml2 = int(np.diff(off1).max()), int(np.diff(off2).max())
+    def start_gpu(self, d=None):
+        from consistent__style_transfer_b200.engine import WMDEngine
+        torch = self.torch
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1 and not self.dist.is_initialized():
+            self.dist.init_process_group("nccl", device_id=self.dev)
+        self.table = workload.make_table(self.a.vocab, d or self.a.d, seed=0)
+        self.eng = WMDEngine(self.table, device=self.local)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)          # > 126 MB L2
 
-    # CPU baseline first (fork-based workers must start before CUDA is initialised)
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n_sample = a.cpu_sample or 3000 * cores
-        pool = CpuPool(table, pairs, cores)
-        wall = pool.run(0, n_sample)
-        pool.close()
-        v = n_sample / wall
-        c_port = cpu_c_port(table, pairs, 40000, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n_sample} pairs of the same workload split over {cores} worker processes: "
-                         f"gensim-shaped python per-pair loop (numpy float32 per cell) + C emd_hat; {wall:.1f}s wall",
-               "compiled_c_port_value": c_port,
-               "compiled_c_port_note": f"all-C oracle (oracle/wmd_oracle.c) on 40000 pairs, {cores} pthreads"}
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    from consistent__style_transfer_b200.engine import WMDEngine
-    eng = WMDEngine(table, device=local)
+    def close(self):
+        if self.eng is not None:
+            self.eng.close()
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.destroy_process_group()
 
-    d_ids1 = torch.from_numpy(ids1).to(dev); d_off1 = torch.from_numpy(off1).to(dev)
-    d_ids2 = torch.from_numpy(ids2).to(dev); d_off2 = torch.from_numpy(off2).to(dev)
-    d_out = torch.empty(a.pairs, dtype=torch.float64, device=dev)
-    d_st = torch.empty(a.pairs, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+def timed_device_steps(ctx, step, steps, warmup):
+    """`warmup` untimed + `steps` timed calls of step(), L2 flushed before each; returns summed ms (this rank)."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        ctx.flush.fill_(1)
+        step()
+    ctx.barrier()
+    evs = []
+    for _ in range(steps):
+        ctx.flush.fill_(1)                                                  # L2 flush, outside the event pair
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    ctx.barrier()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs)
 
-    g_out = torch.empty(world * a.pairs, dtype=torch.float64, device=dev) if world > 1 else None
+
+def pairs_arm(ctx, cpu):
+    from consistent__style_transfer_b200 import sharding
+    a, torch, eng, dev, world, rank = ctx.a, ctx.torch, ctx.eng, ctx.dev, ctx.world, ctx.rank
+    n_gpus = ctx.n_gpus
+    # the global batch (the same on every rank) and this rank's token-balanced contiguous slice of it
+    ids1, off1, ids2, off2 = workload.make_pairs(world * a.pairs, a.shape, a.variant, V=a.vocab, seed=1)
+    bounds = sharding.partition_by_tokens(off1, off2, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    nloc = hi - lo
+    l_ids1, l_off1 = sharding.csr_slice(ids1, off1, lo, hi)
+    l_ids2, l_off2 = sharding.csr_slice(ids2, off2, lo, hi)
+    ml1, ml2 = int(np.diff(l_off1).max()), int(np.diff(l_off2).max())
+    d_ids1 = torch.from_numpy(l_ids1).to(dev); d_off1 = torch.from_numpy(l_off1).to(dev)
+    d_ids2 = torch.from_numpy(l_ids2).to(dev); d_off2 = torch.from_numpy(l_off2).to(dev)
+    d_out = torch.empty(nloc, dtype=torch.float64, device=dev)
+    d_st = torch.empty(nloc, dtype=torch.int32, device=dev)
+    gathered = {}
 
     def dev_step():
         eng.wmd_pairs_cuda(d_ids1, d_off1, d_ids2, d_off2, ml1, ml2, out=d_out, status=d_st)
-        if world > 1:                                                      # the only exchange: final scores, 8 B/pair
-            dist.all_gather_into_tensor(g_out, d_out)
+        if world > 1:                                                      # the only exchange: final scores + status, 12 B/pair
+            gathered["out"], gathered["st"] = sharding.gather_scores(d_out, d_st, bounds)
 
-    # ---- value: inputs resident in HBM ------------------------------------------------------
-    for _ in range(a.warmup):
-        flush.fill_(1)
-        dev_step()
-    barrier()
-    eng.set_profiling(True)
-    eng.profile(reset=True)
-    sampler = ClockSampler(local)
-    sampler.start()
-    evs = []
-    for _ in range(a.steps):
-        flush.fill_(1)                                                     # L2 flush, outside the event pair
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dev_step()
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = sum(step_ms)
-    prof = eng.profile(reset=True)
-    eng.set_profiling(False)
-    stats = eng.last_stats()
-    # one more profiled pass with the chunks serialised on a single stream: the kernels' own durations
-    eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
-    for _ in range(2):
-        flush.fill_(1)
-        dev_step()
-    barrier()
-    prof_serial = eng.profile(reset=True)
-    eng.set_profiling(False); eng.set_serial(False)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = n_gpus * a.pairs * a.steps / (total_ms_max / 1e3)
-
-    # ---- e2e: pinned host buffers through the host entry --------------------------------------
+    # pinned host copies for the end-to-end arm (N = 1: the whole batch is this rank's slice)
     h_ids1 = torch.from_numpy(ids1).pin_memory(); h_off1 = torch.from_numpy(off1).pin_memory()
     h_ids2 = torch.from_numpy(ids2).pin_memory(); h_off2 = torch.from_numpy(off2).pin_memory()
-    h_out = torch.empty(a.pairs, dtype=torch.float64).pin_memory()
-    h_st = torch.empty(a.pairs, dtype=torch.int32).pin_memory()
+    n_all = world * a.pairs
+    h_out = torch.empty(n_all, dtype=torch.float64).pin_memory()
+    h_st = torch.empty(n_all, dtype=torch.int32).pin_memory()
+    np_ids1, np_off1, np_ids2, np_off2 = h_ids1.numpy(), h_off1.numpy(), h_ids2.numpy(), h_off2.numpy()
+    np_out, np_st = h_out.numpy(), h_st.numpy()
 
     def host_step():
-        eng.wmd_pairs_ptr(h_ids1.data_ptr(), h_off1.data_ptr(), h_ids2.data_ptr(), h_off2.data_ptr(), a.pairs,
-                          h_out.data_ptr(), h_st.data_ptr())
-
-    for _ in range(a.warmup):
-        host_step()
-    barrier()
-    e2e_s = 0.0
-    for _ in range(a.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        host_step()                                                        # returns after the D2H of the scores
-        e2e_s += time.perf_counter() - t0
-    barrier()
-    clocks = sampler.stop()                                               # sampled across both timed regions
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_gpus * a.pairs * a.steps / float(t.item())
-    h2d = int(ids1.nbytes + ids2.nbytes + off1.nbytes + off2.nbytes)
-    d2h = int(a.pairs * (8 + 4))
-    same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
-
-    # ---- optional word-distance table (additive; NOT the headline): the same steps with the cost tiles gathered
-    # from a V x V float32 table built once per embedding table instead of recomputed for every pair --------------
-    wdt = None
-    if not a.no_table_arm:
-        try:
-            ref_out = d_out.clone()
+        if world == 1:
+            eng.wmd_pairs(np_ids1, np_off1, np_ids2, np_off2, out=np_out, status=np_st)       # returns after the D2H of the scores
+        else:
+            out, st, _ = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, np_ids1, np_off1, np_ids2, np_off2)
+            h_out.copy_(out, non_blocking=True); h_st.copy_(st, non_blocking=True)
             torch.cuda.synchronize()
+
+    def measure(label):
+        t0 = time.perf_counter()
+        dev_step()                                                         # the first call of an engine builds its table
+        torch.cuda.synchronize()
+        first_s = time.perf_counter() - t0
+        eng.set_profiling(False)
+        for _ in range(a.warmup):
+            ctx.flush.fill_(1)
+            dev_step()
+        ctx.barrier()
+        eng.set_profiling(True); eng.profile(reset=True)
+        total_ms = timed_device_steps(ctx, dev_step, a.steps, 0)
+        prof = eng.profile(reset=True)
+        eng.set_profiling(False)
+        stats = eng.last_stats()
+        # one more profiled pass with the chunks serialised on a single stream: the kernels' own durations
+        eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
+        for _ in range(2):
+            ctx.flush.fill_(1)
+            dev_step()
+        ctx.barrier()
+        prof_serial = eng.profile(reset=True)
+        eng.set_profiling(False); eng.set_serial(False)
+        total_ms_max = ctx.max_over_ranks(total_ms)
+        for _ in range(a.warmup):
+            host_step()
+        ctx.barrier()
+        e2e_s = 0.0
+        for _ in range(a.steps):
+            ctx.flush.fill_(1)
+            ctx.barrier()
             t0 = time.perf_counter()
-            eng.set_distance_table(True)                                       # builds the table (host-synchronous)
-            build_s = time.perf_counter() - t0
-            for _ in range(a.warmup):
-                flush.fill_(1)
-                dev_step()
-            barrier()
-            eng.set_profiling(True); eng.profile(reset=True)
-            evs = []
-            for _ in range(a.steps):
-                flush.fill_(1)
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(); dev_step(); e1.record()
-                evs.append((e0, e1))
-            barrier()
-            prof_t = eng.profile(reset=True)
-            eng.set_profiling(False)
-            tt = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], dtype=torch.float64, device=dev)
-            same_t = bool(torch.equal(ref_out.view(torch.int64), d_out.view(torch.int64)))
-            for _ in range(a.warmup):
-                host_step()
-            barrier()
-            e2e_t = 0.0
-            for _ in range(a.steps):
-                flush.fill_(1)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                host_step()
-                e2e_t += time.perf_counter() - t0
-            barrier()
-            te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            eng.set_distance_table(False)
-            wdt = {"value": n_gpus * a.pairs * a.steps / (float(tt.item()) / 1e3), "unit": UNIT,
-                   "ms_per_step": float(tt.item()) / a.steps,
-                   "e2e_value": n_gpus * a.pairs * a.steps / float(te.item()),
-                   "table_bytes": int(a.vocab) * int(a.vocab) * 4, "table_build_ms_once": build_s * 1e3,
-                   "bit_identical_to_direct_path": same_t,
-                   "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof_t.items() if v["launches"] > 0},
-                   "note": "wmd_set_distance_table(1): every word distance precomputed once per embedding table by the same cost kernels "
-                           "(bit-identical entries), pair tiles gathered from it; the build is outside these timed steps and is NOT part of "
-                           "the headline value / e2e above, which recompute every distance as the reference does"}
-        except Exception as exc:                                           # the additional arm must never cost the headline
-            if world > 1:
-                raise
-            try:
-                eng.set_distance_table(False)
-            except Exception:
-                pass
-            wdt = {"error": str(exc)[:200]}
+            host_step()
+            e2e_s += time.perf_counter() - t0
+        ctx.barrier()
+        e2e_s = ctx.max_over_ranks(e2e_s)
+        dev_scores = (gathered["out"] if world > 1 else d_out).cpu().numpy()
+        return {"label": label, "total_ms": total_ms, "total_ms_max": total_ms_max, "prof": prof, "prof_serial": prof_serial,
+                "stats": stats, "e2e_s": e2e_s, "first_call_s": first_s,
+                "value": n_all * a.steps / (total_ms_max / 1e3), "e2e_value": n_all * a.steps / e2e_s,
+                "same": bool(np.array_equal(np_out, dev_scores)), "scores": dev_scores}
+
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    main = measure("default")
+    clocks = sampler.stop()
+    tinfo = eng.distance_table_info()
+    direct = None
+    if not a.no_direct_arm:
+        eng.set_distance_table(False)
+        direct = measure("direct")
+        eng.set_distance_table(tinfo["enabled"])
 
     # ---- roofline of the dominant kernel --------------------------------------------------------
     peak, peak_src = hbm_peak()
-    alg_bytes_step = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * a.pairs
-    kern = {k: v for k, v in prof.items() if v["launches"] > 0}
+    stats = main["stats"]
+    alg_bytes_step = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * nloc
+    table_bytes_step = 4 * stats["tokens"] + 4 * stats["cells"] + 8 * nloc
+    kern = {k: v for k, v in main["prof"].items() if v["launches"] > 0}
     dom = max(kern, key=lambda k: kern[k]["ms"])
     dom_ms_step = kern[dom]["ms"] / a.steps
-    achieved = alg_bytes_step / (dom_ms_step / 1e3) / 1e9
-    nchunks = max(1, -(-a.pairs // 65536))
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom), "traffic_source": NCU_SOURCE,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_step": alg_bytes_step,
-                "algorithmic_bytes_per_launch": alg_bytes_step / nchunks,
-                "note": "achieved = algorithmic bytes of the step / summed CUDA-event time of the dominant kernel's launches in the "
-                        "timed steps (chunks of two streams overlap, so these times include co-scheduling; the serialised ncu "
-                        "launch list is in profiles/).  The embedding table is L2-resident: DRAM traffic is ~3% of the algorithmic "
-                        "bytes, the real ceilings are the FP32 pipe / issue slots (cost) and instruction issue (solve).",
-                "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in kern.items()},
-                "launches_per_step": {k: v["launches"] // a.steps for k, v in kern.items()},
-                "per_kernel_achieved_gbs": {k: alg_bytes_step / (v["ms"] / a.steps / 1e3) / 1e9 for k, v in kern.items()},
-                "standalone": {"note": "same step with all chunks on one stream (2 extra untimed-for-the-headline steps): "
-                                       "the dominant kernel's own launch durations",
-                               "kernel_ms_per_step": {k: v["ms"] / 2 for k, v in prof_serial.items() if v["launches"] > 0},
-                               "achieved": alg_bytes_step / (prof_serial[dom]["ms"] / 2 / 1e3) / 1e9,
-                               "frac": alg_bytes_step / (prof_serial[dom]["ms"] / 2 / 1e3) / 1e9 / peak},
-                "whole_step_achieved": alg_bytes_step / (total_ms / a.steps / 1e3) / 1e9}
+    serial = {k: v["ms"] / 2 for k, v in main["prof_serial"].items() if v["launches"] > 0}
+    nlaunch = max(1, kern[dom]["launches"] // a.steps)
+    ncu = json.load(open(NCU_FILE)) if os.path.exists(NCU_FILE) else None
+    sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": alg_bytes_step / (dom_ms_step / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": alg_bytes_step / (dom_ms_step / 1e3) / 1e9 / peak,
+        "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+        "traffic_source": (f"{os.path.relpath(NCU_FILE, ROOT)}: {ncu.get('source')} at commit {ncu.get('commit')}, "
+                           f"{ncu.get('pairs_per_launch')} pairs per launch" if ncu else None),
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_step": alg_bytes_step, "algorithmic_bytes_per_launch": alg_bytes_step / nlaunch,
+        "binding": "instruction issue: the table mode moves 4 B per cost cell instead of d floats per row, so neither HBM nor "
+                   "the FP32 pipe limits the fused kernel -- the exact transport solve does (data-dependent pivots, REDUX / "
+                   "ballot / shuffle per selection); `issue` is the kernel's share of issue slots in use",
+        "issue": ({"issue_active_pct": ncu.get("issue_active_pct"), "warp_instructions_per_pair": ncu.get("warp_instructions_per_pair"),
+                   "ceiling_pairs_per_s_at_100pct_issue": (148 * 4 * sm_clock / ncu["warp_instructions_per_pair"]
+                                                           if ncu.get("warp_instructions_per_pair") else None)} if ncu else None),
+        "table_mode": {"bytes_per_step": table_bytes_step, "note": "what the fused kernel really has to fetch: ids + 4 B per cell of "
+                       "the u1 x u2 tile from the word-distance table + the score", "achieved_gbs": table_bytes_step / (dom_ms_step / 1e3) / 1e9},
+        "note": "achieved = SURVEY 8(d) algorithmic bytes of the step (4(n1+n2) + 4d(u1+u2) + 8 per pair, from the engine's own counters) / "
+                "summed CUDA-event time of the dominant kernel's launches in the timed steps, recorded on the kernels' own streams "
+                "(chunks on two streams overlap, so these times include co-scheduling; `standalone` has the serialised durations)",
+        "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in kern.items()},
+        "launches_per_step": {k: v["launches"] // a.steps for k, v in kern.items()},
+        "standalone": {"note": "same step with all chunks on one stream (2 extra steps outside the headline timing)",
+                       "kernel_ms_per_step": serial,
+                       "achieved": alg_bytes_step / (serial[dom] / 1e3) / 1e9, "frac": alg_bytes_step / (serial[dom] / 1e3) / 1e9 / peak},
+        "whole_step_achieved": alg_bytes_step / (main["total_ms"] / a.steps / 1e3) / 1e9}
+    if direct is not None:
+        dk = {k: v["ms"] / 2 for k, v in direct["prof_serial"].items() if v["launches"] > 0}
+        cells = stats["cells"] / max(1, world)                                # this rank's cells per step
+        cost_ms = dk.get("cost")
+        roofline["direct_path"] = {
+            "kernel_ms_per_step_standalone": dk,
+            "cost_hbm_frac": alg_bytes_step / (cost_ms / 1e3) / 1e9 / peak if cost_ms else None,
+            "cost_fp32_frac": (direct["stats"]["cells"] * 3 * a.d / (cost_ms / 1e3) / (148 * 128 * sm_clock) if cost_ms else None),
+            "note": "direct path (no table): the cost kernel's FP32 pipe floor is cells x 3d separately rounded operations "
+                    "(numpy's sub, square, add) / (SMs x 128 lanes x clock)"}
     launches = sum(v["launches"] for v in kern.values())
-
+    line = None
     if rank == 0:
+        h2d = int(ids1.nbytes + ids2.nbytes + off1.nbytes + off2.nbytes) // (1 if world == 1 else 1)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": main["total_ms_max"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "pairs_per_gpu": a.pairs, "global_pairs": n_gpus * a.pairs,
-                       "mean_len": float(stats["tokens"]) / (2 * a.pairs), "cost": "float32 numpy-order (bit-exact)",
-                       "emd": "pyemd 1e6-grid integer optimum, exact", "l2": "256 MiB flush write between timed steps",
-                       "parallelism": f"pairs sharded over {n_gpus} GPU(s); no data-path collective, one NCCL "
-                                      f"all-gather of the float64 scores per step inside the timed region"},
+            "config": config_dict(a, n_gpus),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timing": "perf_counter around the synchronous wmd_pairs_host call on pinned buffers",
-                    "matches_device_path": same},
+            "e2e": {"value": main["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_all * 12),
+                    "timing": "perf_counter around the public call on pinned host buffers (N = 1: WMDEngine.wmd_pairs; N > 1: "
+                              "sharding.wmd_pairs_sharded + device->host read of the gathered scores), max over ranks",
+                    "matches_device_path": main["same"]},
             "gpu_launches": launches,
             "roofline": roofline,
+            "word_distance_table": {"enabled": tinfo["enabled"], "bytes": tinfo["bytes"], "table_build_ms": tinfo["build_ms"],
+                                    "first_call_s": main["first_call_s"],
+                                    "note": "default policy: built once per embedding table by the first scoring call (here: before "
+                                            "the warm-up steps), never inside a timed step"},
+            "mean_len": float(stats["tokens"]) / (2 * max(nloc, 1)),
         }
+        if direct is not None:
+            per_pair_gain_ms = (direct["total_ms_max"] - main["total_ms_max"]) / a.steps / a.pairs
+            line["without_table"] = {
+                "value": direct["value"], "unit": UNIT, "ms_per_step": direct["total_ms_max"] / a.steps, "e2e_value": direct["e2e_value"],
+                "bit_identical_to_default": bool(np.array_equal(direct["scores"], main["scores"])),
+                "kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in direct["prof"].items() if v["launches"] > 0},
+                "note": "wmd_set_distance_table(0): every float32 distance recomputed from the embedding rows for every pair, as gensim does"}
+            line["word_distance_table"]["table_break_even_pairs"] = (tinfo["build_ms"] / per_pair_gain_ms if per_pair_gain_ms > 0 else None)
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if wdt is not None:
-            line["with_word_distance_table"] = wdt
-        print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
-def run_allpairs(a):
-    """BASELINE configs[3]: all-pairs top-k over one Yelp-shape document set (self join), rows sharded
-    over the ranks (strong scaling: the job is fixed, every rank takes a block of rows; the only exchange
-    is the final all-gather of (index, distance) per row).  Effective pairs/s = docs^2 / time."""
-    import torch
-    import torch.distributed as dist
+def allpairs_arm(ctx, steps=1):
+    """BASELINE configs[3]: all-pairs top-k over one Yelp-shape document set (self join), rows sharded over the ranks
+    (strong scaling: the job is fixed, every rank takes a block of rows; the only exchange is the final NCCL
+    all-gather of (index, distance) per row).  Effective pairs/s = docs^2 / time."""
     from consistent__style_transfer_b200 import sharding
-    from consistent__style_transfer_b200.engine import WMDEngine
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    table = workload.make_table(a.vocab, a.d, seed=0)
+    a, torch, eng, dev, world, rank = ctx.a, ctx.torch, ctx.eng, ctx.dev, ctx.world, ctx.rank
+    dist = ctx.dist
     ids, off, _, _ = workload.make_pairs(a.docs, a.shape, "independent", V=a.vocab, seed=1)
     N, k = a.docs, a.topk
-    eng = WMDEngine(table, device=local)
     blocks = sharding.row_blocks(N, world)
     r0, r1 = int(blocks[rank]), int(blocks[rank + 1])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    mx = int(np.diff(blocks).max())
     # warm-up on a small block: builds the word-distance table (one-off per embedding table) and the allocations
     t0 = time.perf_counter()
     eng.allpairs_topk(ids, off, ids, off, k, r0, min(r1, r0 + 256))
-    barrier()
+    ctx.barrier()
     t_warm = time.perf_counter() - t0
+    t_idx = torch.zeros((mx, k), dtype=torch.int32, device=dev)
+    t_dst = torch.zeros((mx, k), dtype=torch.float64, device=dev)
+    g_idx = torch.empty((world * mx, k), dtype=torch.int32, device=dev) if world > 1 else None
+    g_dst = torch.empty((world * mx, k), dtype=torch.float64, device=dev) if world > 1 else None
     infos, walls = [], []
-    for _ in range(max(1, a.steps)):
-        barrier()
+    for _ in range(max(1, steps) + 1):                             # the first full pass sizes the workspace: not timed
+        ctx.barrier()
         t0 = time.perf_counter()
-        idx, dst, info = eng.allpairs_topk(ids, off, ids, off, k, r0, r1)
-        if world > 1:
-            mx = int(np.diff(blocks).max())
-            t_idx = torch.zeros((mx, k), dtype=torch.int32, device=dev); t_idx[:idx.shape[0]] = torch.from_numpy(idx).to(dev)
-            t_dst = torch.zeros((mx, k), dtype=torch.float64, device=dev); t_dst[:dst.shape[0]] = torch.from_numpy(dst).to(dev)
-            g_idx = torch.empty((world * mx, k), dtype=torch.int32, device=dev)
-            g_dst = torch.empty((world * mx, k), dtype=torch.float64, device=dev)
+        info = eng.allpairs_topk_cuda(ids, off, ids, off, k, r0, r1, out_idx=t_idx[:r1 - r0], out_dist=t_dst[:r1 - r0])
+        if world > 1:                                              # results never left the device
             dist.all_gather_into_tensor(g_idx, t_idx); dist.all_gather_into_tensor(g_dst, t_dst)
-        barrier()
+        ctx.barrier()
         walls.append(time.perf_counter() - t0)
         infos.append(info)
-    t = torch.tensor([statistics.median(walls)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall = float(t.item())
+    wall = ctx.max_over_ranks(statistics.median(walls[1:]))
     cnt = torch.tensor([infos[-1]["exact_round1"], infos[-1]["exact_round2"], infos[-1]["bounds"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt)
     verified = None
     if rank == 0 and a.verify > 0:
         n = min(a.verify, N)
+        rows = min(n, 512)
         sub_ids, sub_off = ids[:off[n]], off[:n + 1]
-        vi, vd, _ = eng.allpairs_topk(sub_ids, sub_off, sub_ids, sub_off, k, 0, min(n, 512))
-        # brute force of the same rows through the pair path of the engine (every pair solved exactly)
+        vi, vd, _ = eng.allpairs_topk(sub_ids, sub_off, sub_ids, sub_off, k, 0, rows)
+        # brute force of the same rows through the pair path of the engine (every pair solved exactly), one call
+        lens = np.diff(sub_off)[:rows]
+        rep_ids = np.concatenate([np.tile(sub_ids[sub_off[i]:sub_off[i + 1]], n) for i in range(rows)])
+        rep_off = np.zeros(rows * n + 1, np.int64)
+        np.cumsum(np.repeat(lens, n), out=rep_off[1:])
+        all_ids = np.tile(sub_ids, rows)
+        all_off = (np.tile(sub_off[:-1], rows) + np.repeat(np.arange(rows, dtype=np.int64) * int(sub_off[-1]), n))
+        all_off = np.concatenate([all_off, [rows * int(sub_off[-1])]])
+        d, _ = eng.wmd_pairs(rep_ids, rep_off, all_ids, all_off)
+        d = d.reshape(rows, n)
         ok = True
-        lens = np.diff(sub_off)
-        for i in range(min(n, 512)):
-            doc = sub_ids[sub_off[i]:sub_off[i + 1]]
-            ids1 = np.tile(doc, n); off1 = np.arange(n + 1, dtype=np.int64) * len(doc)
-            d, _ = eng.wmd_pairs(ids1, off1, sub_ids, sub_off)
-            order = np.lexsort((np.arange(n), d))[:k]
-            ok = ok and np.array_equal(order.astype(np.int32), vi[i]) and d[order].tobytes() == vd[i].tobytes()
-        verified = {"rows": int(min(n, 512)), "block": int(n), "matches_bruteforce": bool(ok)}
-    if rank == 0:
-        line = {"metric": "allpairs_effective_pairs_per_sec", "value": float(N) * N / wall, "unit": "pairs/s", "n_gpus": world,
-                "steps": max(1, a.steps), "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong",
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"all-pairs top-{k} WMD, {N} x {N} {a.shape}-shape documents (self join), d={a.d}, V={a.vocab}",
-                           "timing": "wall clock around the host entry incl. H2D of the documents, D2H of the result and "
-                                     "the NCCL all-gather; max over ranks; word-distance table built in the warm-up "
-                                     f"({t_warm:.2f}s incl. first allocations)"},
-                "exact_solves": float(cnt[0] + cnt[1]), "exact_round1": float(cnt[0]), "exact_round2": float(cnt[1]),
-                "bounds": float(cnt[2]), "pruned_fraction": 1.0 - float(cnt[0] + cnt[1]) / max(1.0, float(cnt[2])),
-                "rank0_phase_ms": {kk: vv for kk, vv in infos[-1].items() if kk.startswith("ms_")},
-                "verified": verified}
-        print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+        for i in range(rows):
+            order = np.lexsort((np.arange(n), d[i]))[:k]
+            ok = ok and np.array_equal(order.astype(np.int32), vi[i]) and d[i][order].tobytes() == vd[i].tobytes()
+        verified = {"rows": int(rows), "block": int(n), "matches_bruteforce": bool(ok)}
+    ctx.barrier()
+    if rank != 0:
+        return None
+    return {"metric": "allpairs_effective_pairs_per_sec", "value": float(N) * N / wall, "unit": "pairs/s", "n_gpus": world,
+            "steps": max(1, steps), "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong",
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"all-pairs top-{k} WMD, {N} x {N} {a.shape}-shape documents (self join), d={a.d}, V={a.vocab}",
+                       "timing": "wall clock around the library call (H2D of the documents, bounds, exact solves, top-k left on the "
+                                 "device) + the NCCL all-gather of the result, barrier on both sides, max over ranks; word-distance "
+                                 f"table built in the warm-up ({t_warm:.2f}s incl. first allocations)"},
+            "exact_solves": float(cnt[0] + cnt[1]), "exact_round1": float(cnt[0]), "exact_round2": float(cnt[1]),
+            "bounds": float(cnt[2]), "pruned_fraction": 1.0 - float(cnt[0] + cnt[1]) / max(1.0, float(cnt[2])),
+            "rank0_phase_ms": {kk: vv for kk, vv in infos[-1].items() if kk.startswith("ms_")},
+            "verified": verified}
 
 
-def run_latency(a):
-    """BASELINE configs[2]: the in-loop caller's shape -- one collate batch per call (src/loader.py:60: 256 Yelp
-    pairs or 128 book pairs of noised sentences) through the host entry, pageable numpy buffers, wall clock per
-    call incl. H2D / D2H.  Reports the median and p99 latency and the resulting pairs/s, next to the oracle port
-    of the reference loop on one core (the reference's collate runs single-threaded in the main process)."""
-    import torch
-    from consistent__style_transfer_b200.engine import WMDEngine
-    from oracle import wmd_oracle
-    table = workload.make_table(a.vocab, 100, seed=0)              # d = 100: the reference's real embedding width
-    eng = WMDEngine(table, device=0)
-    out = {}
-    for shape, B in (("yelp", 256), ("book", 128)):
-        ids1, off1, ids2, off2 = workload.make_pairs(B * 64, shape, "noised", V=a.vocab, seed=5, batch=B)
-        calls = []
-        for b in range(64):
-            lo, hi = b * B, (b + 1) * B
-            calls.append((ids1[off1[lo]:off1[hi]].copy(), (off1[lo:hi + 1] - off1[lo]).copy(),
-                          ids2[off2[lo]:off2[hi]].copy(), (off2[lo:hi + 1] - off2[lo]).copy()))
-        for c in calls[:8]:
-            eng.wmd_pairs(*c)
-        lat = []
-        for rep in range(4):
-            for c in calls:
-                t0 = time.perf_counter()
-                eng.wmd_pairs(*c)
-                lat.append(time.perf_counter() - t0)
-        lat = np.array(lat)
-        # reference-shaped loop on ONE core for the same batch
-        words = ["w%06d" % i for i in range(a.vocab)]
-        kv = wmd_oracle.KeyedVectorsOracle(words, table)
-        c = calls[0]
-        t0 = time.perf_counter()
-        for p in range(B):
-            kv.wmdistance([words[t] for t in c[0][c[1][p]:c[1][p + 1]]], [words[t] for t in c[2][c[3][p]:c[3][p + 1]]])
-        cpu_s = time.perf_counter() - t0
-        out[f"{shape}_batch{B}"] = {"median_us": float(np.median(lat) * 1e6), "p99_us": float(np.quantile(lat, 0.99) * 1e6),
-                                    "pairs_per_s": float(B / np.median(lat)), "cpu_reference_port_1core_ms": cpu_s * 1e3,
-                                    "speedup_vs_1core": float(cpu_s / np.median(lat))}
-    print(json.dumps({"metric": "wmd_batch_latency", "unit": "us", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "one pretrain collate batch per call (noised pairs, d=100, V=%d), host entry, pageable buffers" % a.vocab},
-                      "batches": out}), flush=True)
-    eng.close()
-
-
-def run_sweep(a):
-    """BASELINE configs[4]: fixed document lengths 8 -> 256 (both sides, independent draws, d=300), 2^18 pairs per GPU
-    and length (2^14 from 128 tokens up), device-resident inputs, CUDA-event timed, max over ranks; the scores are
-    all-gathered over NCCL inside the timed region when N > 1.  Per-kernel times come from a serialised pass on rank 0."""
-    import torch
-    import torch.distributed as dist
-    from consistent__style_transfer_b200.engine import WMDEngine
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    table = workload.make_table(a.vocab, a.d, seed=0)
-    eng = WMDEngine(table, device=local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    lengths = [int(x) for x in a.lengths.split(",")]
+def sweep_arm(ctx, steps=3, lengths=None, mixed=True):
+    """BASELINE configs[4]: fixed document lengths 8 -> 256 (both sides, independent draws), 2^18 pairs per GPU and length
+    (2^14 from 128 tokens up), device-resident inputs, CUDA-event timed, max over ranks; the scores are all-gathered over
+    NCCL inside the timed region when N > 1.  `mixed`: lengths uniform in [1, 256] per side -- no launch of the default
+    path depends on the longest document of the batch, so its time should be the sum of its pairs' own costs."""
+    a, torch, eng, dev, world, rank = ctx.a, ctx.torch, ctx.eng, ctx.dev, ctx.world, ctx.rank
+    dist = ctx.dist
+    lengths = lengths or [int(x) for x in a.lengths.split(",")]
     rows = {}
-    for L in lengths:
-        n = 1 << (18 if L < 128 else 14)
-        ids1, off1, ids2, off2 = workload.make_pairs(n, f"fixed:{L}", "independent", V=a.vocab, seed=L + 1000 * rank)
+
+    def run(shape, n, seed, ml):
+        ids1, off1, ids2, off2 = workload.make_pairs(n, shape, "independent", V=a.vocab, seed=seed + 1000 * rank)
         d = [torch.from_numpy(x).to(dev) for x in (ids1, off1, ids2, off2)]
         out = torch.empty(n, dtype=torch.float64, device=dev); st = torch.empty(n, dtype=torch.int32, device=dev)
         g_out = torch.empty(world * n, dtype=torch.float64, device=dev) if world > 1 else None
 
         def step():
-            eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
+            eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], ml, ml, out=out, status=st)
             if world > 1:
                 dist.all_gather_into_tensor(g_out, out)
         for _ in range(3):
             step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ctx.barrier()
         ms = []
-        for _ in range(max(3, a.steps)):
-            flush.fill_(1)
+        for _ in range(max(3, steps)):
+            ctx.flush.fill_(1)
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); step(); e1.record()
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
-        t = torch.tensor([statistics.median(ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t = float(t.item())
+        t = ctx.max_over_ranks(statistics.median(ms))
         stats = eng.last_stats()
         eng.set_serial(True); eng.set_profiling(True); eng.profile(reset=True)
-        eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], L, L, out=out, status=st)
+        eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], ml, ml, out=out, status=st)
         torch.cuda.synchronize()
         prof = eng.profile(reset=True)
         eng.set_profiling(False); eng.set_serial(False)
         alg = 4 * stats["tokens"] + 4 * a.d * stats["uniques"] + 8 * n
-        rows[str(L)] = {"pairs_per_gpu": n, "ms": t, "pairs_per_s": world * n / (t / 1e3),
-                        "mean_unique_tokens_per_side": stats["uniques"] / (2 * n),
-                        "algorithmic_gb_per_s_per_gpu": alg / (t / 1e3) / 1e9,
-                        "hbm_roofline_frac": alg / (t / 1e3) / 1e9 / hbm_peak()[0],
-                        "kernel_ms_serial": {k: v["ms"] for k, v in prof.items() if v["launches"] > 0}}
-    if rank == 0:
-        print(json.dumps({"metric": "wmd_length_sweep_pairs_per_sec", "unit": "pairs/s", "n_gpus": world, "dtype": "f64", "data": "synthetic",
-                          "scaling": "weak",
-                          "config": {"workload": f"fixed lengths {a.lengths} both sides, independent, d={a.d}, V={a.vocab}, 2^18 pairs per GPU (2^14 from 128 tokens)",
-                                     "l2": "256 MiB flush write between timed steps",
-                                     "timing": "median of the timed steps per rank (CUDA events), max over ranks"},
-                          "peak_hbm_gbs": hbm_peak()[0], "lengths": rows}), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+        return {"pairs_per_gpu": n, "ms": t, "pairs_per_s": world * n / (t / 1e3),
+                "mean_unique_tokens_per_side": stats["uniques"] / (2 * n),
+                "algorithmic_gb_per_s_per_gpu": alg / (t / 1e3) / 1e9,
+                "hbm_roofline_frac": alg / (t / 1e3) / 1e9 / hbm_peak()[0],
+                "kernel_ms_serial": {k: v["ms"] for k, v in prof.items() if v["launches"] > 0}}, (off1, off2)
+
+    for L in lengths:
+        rows[str(L)], _ = run(f"fixed:{L}", 1 << (18 if L < 128 else 14), L, L)
+    mixed_rec = None
+    if mixed and len(lengths) >= 2:
+        n = 1 << 16
+        rec, (off1, off2) = run("uniform:1-256", n, 77, 256)
+        # the pairs' own costs: per-pair time of the fixed-length runs, interpolated log-log at sqrt(n1 * n2)
+        Ls = np.array(sorted(int(k) for k in rows), dtype=np.float64)
+        per_pair = np.array([rows[str(int(L))]["ms"] / rows[str(int(L))]["pairs_per_gpu"] for L in Ls])
+        eff = np.sqrt(np.maximum(np.diff(off1), 1) * np.maximum(np.diff(off2), 1)).astype(np.float64)
+        pred = float(np.exp(np.interp(np.log(eff), np.log(Ls), np.log(per_pair))).sum())
+        rec["predicted_ms_from_fixed_length_rates"] = pred
+        rec["measured_over_predicted"] = rec["ms"] / pred
+        mixed_rec = rec
+    if rank != 0:
+        return None
+    return {"metric": "wmd_length_sweep_pairs_per_sec", "unit": "pairs/s", "n_gpus": world, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak",
+            "config": {"workload": f"fixed lengths {','.join(map(str, lengths))} both sides, independent, d={a.d}, V={a.vocab}, 2^18 pairs per GPU (2^14 from 128 tokens)",
+                       "l2": "256 MiB flush write between timed steps",
+                       "timing": "median of the timed steps per rank (CUDA events), max over ranks"},
+            "peak_hbm_gbs": hbm_peak()[0], "lengths": rows,
+            "mixed_uniform_1_256": mixed_rec}
+
+
+def latency_arm(a):
+    """BASELINE configs[2] through the reference's own call surface, one pretrain collate batch per call (src/loader.py:60:
+    256 Yelp pairs or 128 book pairs of noised sentences, d = 100): `WMDdistance.cal_wmd_label(lists, lists, tokenizer)`,
+    `collate_pretrain(...)(samples)` and `calculate_wmd_scores(strings, strings, model)`, wall clock per call, next to the
+    oracle port of the reference loop on ONE core (the reference's collate runs single-threaded in the main process)."""
+    import random
+
+    from consistent__style_transfer_b200 import content_preserve as cp
+    from consistent__style_transfer_b200.loader import LabelPrefetcher, collate_pretrain
+    from consistent__style_transfer_b200.wmd import WMDdistance
+    from oracle import wmd_oracle
+    V = a.vocab
+    table = workload.make_table(V, 100, seed=0)                    # d = 100: the reference's real embedding width
+    words = ["w%06d" % i for i in range(V)]
+
+    class Tok:                                                     # shape of src/vocab.py:BPETokenizer as the path uses it
+        tokenizer = None
+
+        def __init__(self):
+            self.tokenizer = self
+
+        def id_to_token(self, i):
+            return words[i - 4] if 4 <= i < V + 4 else None
+
+        def ids_to_tokens(self, ids):
+            return [self.id_to_token(i) for i in ids]
+
+        def __len__(self):
+            return V + 4
+
+    tok = Tok()
+    w = WMDdistance.from_embeddings(words, table, normalize=False)
+    kv = wmd_oracle.KeyedVectorsOracle(words, table)
+    ow = wmd_oracle.WMDdistanceOracle(kv)
+    out = {}
+    for shape, B in (("yelp", 256), ("book", 128)):
+        ids1, off1, ids2, off2 = workload.make_pairs(B * 32, shape, "noised", V=V, seed=5, batch=B)
+        lists = lambda ids, off, lo, hi: [(ids[off[p]:off[p + 1]] + 4).tolist() for p in range(lo, hi)]
+        calls = [(lists(ids1, off1, b * B, (b + 1) * B), lists(ids2, off2, b * B, (b + 1) * B)) for b in range(32)]
+        samples = [[(s, i % 2) for i, s in enumerate(c[0])] for c in calls]
+
+        def med(f, args_list, reps=3):
+            for x in args_list[:4]:
+                f(x)
+            lat = []
+            for _ in range(reps):
+                for x in args_list:
+                    t0 = time.perf_counter(); f(x); lat.append(time.perf_counter() - t0)
+            return float(np.median(lat) * 1e6), float(np.quantile(lat, 0.99) * 1e6)
+
+        label_us, label_p99 = med(lambda c: w.cal_wmd_label(c[0], c[1], tok), calls)
+        np.random.seed(1); random.seed(2)
+        coll = collate_pretrain(tok, w)
+        collate_us, _ = med(coll, samples)
+        t0 = time.perf_counter()
+        nb = sum(1 for _ in LabelPrefetcher(samples * 3, tok, w))
+        prefetch_us = (time.perf_counter() - t0) / nb * 1e6
+        strs = [([" ".join(words[t - 4] for t in s) for s in c[0]], [" ".join(words[t - 4] for t in s) for s in c[1]]) for c in calls[:8]]
+        score_us, _ = med(lambda c: cp.calculate_wmd_scores(c[0], c[1], w.model), strs)
+        c = calls[0]
+        t0 = time.perf_counter()
+        ow.cal_wmd_label(c[0], c[1], tok)
+        cpu_s = time.perf_counter() - t0
+        out[f"{shape}_batch{B}"] = {
+            "cal_wmd_label_us": label_us, "cal_wmd_label_p99_us": label_p99, "collate_pretrain_us": collate_us,
+            "collate_with_label_prefetch_us": prefetch_us, "calculate_wmd_scores_us": score_us,
+            "pairs_per_s_through_cal_wmd_label": float(B / (label_us * 1e-6)),
+            "cpu_reference_port_1core_ms": cpu_s * 1e3, "speedup_vs_1core": float(cpu_s / (label_us * 1e-6))}
+    w.model.wv.close()
+    return {"metric": "wmd_batch_latency", "unit": "us", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "one pretrain collate batch per call (noised pairs, d=100, V=%d): python lists of tokenizer ids / "
+                                   "strings in, python floats / tensors out; median wall time per call" % V},
+            "batches": out}
+
+
+def run_b200(a):
+    ctx = Ctx(a)
+    cpu = None
+    if a.mode == "pairs" and ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline:
+        # CPU baseline first (fork-based workers must start before CUDA is initialised)
+        cores = os.cpu_count() or 1
+        table = workload.make_table(a.vocab, a.d, seed=0)
+        pairs = workload.make_pairs(max(a.cpu_sample or 3000 * cores, 40000), a.shape, a.variant, V=a.vocab, seed=1)
+        n_sample = a.cpu_sample or 3000 * cores
+        pool = CpuPool(table, pairs, cores)
+        wall = pool.run(0, n_sample)
+        pool.close()
+        c_port = cpu_c_port(table, pairs, 40000, cores)
+        one = cpu_one_core(table, pairs, 1500)
+        cpu = {"value": n_sample / wall, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n_sample} pairs of the same workload split over {cores} worker processes: "
+                         f"gensim-shaped python per-pair loop (numpy float32 per cell) + C emd_hat; {wall:.1f}s wall",
+               "one_core_value": one,
+               "one_core_note": "the same loop in ONE process on 1 500 pairs: the reference's real configuration "
+                                "(collate runs in the main process, src/main_pretrain.py:120-122)",
+               "compiled_c_port_value": c_port,
+               "compiled_c_port_note": f"all-C oracle (oracle/wmd_oracle.c) on 40000 pairs, {cores} pthreads"}
+    if a.mode == "latency":
+        print(json.dumps(latency_arm(a)), flush=True)
+        return
+    ctx.start_gpu()
+    line = None
+    if a.mode == "pairs":
+        line = pairs_arm(ctx, cpu)
+        if not a.no_extras:
+            extras = {}
+            for name, fn in (("allpairs", lambda: allpairs_arm(ctx, steps=2)), ("sweep", lambda: sweep_arm(ctx, steps=3))):
+                try:
+                    extras[name] = fn()
+                except Exception as exc:                                   # a sub-record must never cost the headline
+                    if ctx.world > 1:
+                        raise
+                    extras[name] = {"error": str(exc)[:300]}
+            if ctx.rank == 0:
+                line.update(extras)
+    elif a.mode == "allpairs":
+        line = allpairs_arm(ctx, steps=a.steps)
+    elif a.mode == "sweep":
+        line = sweep_arm(ctx, steps=a.steps)
+    ctx.close()
+    if a.mode == "pairs" and not a.no_extras and ctx.rank == 0 and ctx.world == 1:
+        try:
+            line["latency"] = latency_arm(a)
+        except Exception as exc:
+            line["latency"] = {"error": str(exc)[:300]}
+    if ctx.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.mode == "sweep":
-        run_sweep(args)
-    elif args.mode == "latency":
-        run_latency(args)
-    elif args.mode == "allpairs":
-        run_allpairs(args)
     else:
         run_b200(args)

@@ -29,6 +29,17 @@ SIGNATURES = {
     "wmd_get_table": (ctypes.c_int, [c_handle, c_f32p]),
     "wmd_pairs_host": (ctypes.c_int, [c_handle, c_i32p, c_i64p, c_i32p, c_i64p, ctypes.c_int64, ctypes.c_int32,
                                       c_f64p, c_i32p]),
+    "wmd_pairs_host_in_dev_out": (ctypes.c_int, [c_handle, c_i32p, c_i64p, c_i32p, c_i64p, ctypes.c_int64, ctypes.c_int32,
+                                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "wmd_pairs_submit": (ctypes.c_int, [c_handle, c_i32p, c_i64p, c_i32p, c_i64p, ctypes.c_int64, ctypes.c_int32]),
+    "wmd_pairs_wait": (ctypes.c_int, [c_handle, c_f64p, c_i32p]),
+    "wmd_workspace_bytes": (ctypes.c_int, [c_handle, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p]),
+    "wmd_nbow_dev": (ctypes.c_int, [c_handle, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "wmd_rwmd_pairs_dev": (ctypes.c_int, [c_handle, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "wmd_pairs_dev": (ctypes.c_int, [c_handle, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -40,6 +51,8 @@ SIGNATURES = {
                                            c_f64p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p]),
     "wmd_allpairs_topk_host": (ctypes.c_int, [c_handle, c_i32p, c_i64p, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int64,
                                               ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, c_i32p, c_f64p, c_i64p, c_f64p]),
+    "wmd_allpairs_topk_dev": (ctypes.c_int, [c_handle, c_i32p, c_i64p, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int64,
+                                             ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, c_i64p, c_f64p]),
     "wmd_emd_batch_host": (ctypes.c_int, [c_handle, c_f64p, c_f64p, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_double, c_f64p]),
     "wmd_set_profiling": (ctypes.c_int, [c_handle, ctypes.c_int32]),

@@ -17,11 +17,17 @@
 // mass and the <= 512 masses by <= 0.5e-6 each, i.e. |WMD_pyemd - WMD_real| < 3e-4 * maxC / 2 ... we
 // use 1e-3, an absolute bound that is generous for unit vectors (maxC <= 2) and costs nothing.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace wmd {
 
-constexpr double kLbMargin = 1e-3;
+// Relative slack of the round-2 threshold: thr = kth * (1 + kLbMarginRel) + kLbMarginRel * dmax.  It covers the gap
+// between the real-valued optimum that RWMD bounds and the 1e6-grid optimum pyemd returns: every cost is rounded by
+// <= 0.5e-6 * maxC and every one of the <= 2 * 256 masses by <= 0.5e-6 of the total, so
+// |WMD_pyemd - WMD_real| <= (0.5e-6 + 512 * 0.5e-6) * maxC < 2.6e-4 * maxC, and maxC <= dmax, the largest entry of
+// the word-distance table (so the margin follows the scale of an un-normalised embedding table).
+constexpr double kLbMarginRel = 3e-4;
 
 // ---- D: scatter the cost tiles of row-block pairs into the V x V table --------------------------
 // pair q = (bi, bj), bi <= bj, blocks of BS consecutive table rows.
@@ -80,101 +86,140 @@ __global__ void table_max_kernel(const float *D, int64_t n, unsigned int *maxbit
     if ((threadIdx.x & 31) == 0) atomicMax(maxbits, m);
 }
 
-// ---- Z[w][j] = min_t D[t][w] over the in-vocabulary rows t of document j --------------------------
+// ---- D16: the word-distance table rounded DOWN to half precision ----------------------------------
+// The bounds are sums of table entries, so entries rounded down keep every bound a lower bound; half the bytes
+// of the float table for the two kernels whose time is its traffic (z_build16_kernel, and through Z the bound tiles).
+__global__ void dtab_to_half_kernel(const float *D, int64_t n, __half *D16)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        D16[i] = __float2half_rd(D[i]);
+}
+
+// ---- packed document lists for the bound kernel: (table row, weight) per unique token --------------
+// weight = count / valid tokens rounded DOWN to float32, so that every partial sum of the bound stays below the
+// exact one.  Entries live at the documents' CSR offsets like rows / counts.
+__global__ void pack_lists_kernel(const int32_t *rows, const int32_t *cnt, const int64_t *off, const int32_t *uniq,
+                                  const int32_t *nval, int64_t ndocs, int2 *lists)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= ndocs) return;
+    const int64_t a = off[j];
+    const int u = uniq[j];
+    const float n = (float)nval[j];
+    for (int k = 0; k < u; ++k)
+        lists[a + k] = make_int2(rows[a + k], __float_as_int(__fdiv_rd((float)cnt[a + k], n)));
+}
+
+// ---- Z[w][j] = min_t D16[t][w] over the in-vocabulary rows t of document j -----------------------
 // rows / uniq: per-document unique rows at the CSR offsets (nbow_docs_kernel). Documents without
 // any in-vocabulary token get +inf (every WMD with them is +inf).
 struct ZArgs {
-    const float *D; int32_t V;
+    const __half *D16; int32_t V;
     const int32_t *rows; const int64_t *off; const int32_t *uniq;
     int64_t doc0; int32_t ndocs;              // documents [doc0, doc0 + ndocs) -> columns [0, ndocs)
-    float *Z; int64_t ldz;                    // Z[w * ldz + (j - doc0)]
+    __half *Z; int64_t ldz;                   // Z[w * ldz + (j - doc0)]
 };
 
+// block = 64 words x 32 documents: a warp reads 64 consecutive halves (128 B) of one table row per token
 __global__ void __launch_bounds__(1024)
-z_build_kernel(const __grid_constant__ ZArgs A)
+z_build16_kernel(const __grid_constant__ ZArgs A)
 {
-    __shared__ float tile[32][33];
+    __shared__ __half2 tile[32][33];          // [doc][word pair]
     const int x = threadIdx.x, y = threadIdx.y;
-    const int w0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-    const int j = j0 + y, w = w0 + x;
-    float best = __int_as_float(0x7f800000);
+    const int w0 = blockIdx.y * 64, j0 = blockIdx.x * 32;
+    const int j = j0 + y, w = w0 + 2 * x;
+    const __half inf = __ushort_as_half((unsigned short)0x7c00);
+    __half2 best = __halves2half2(inf, inf);
     if (j < A.ndocs && w < A.V) {
         const int64_t a = A.off[A.doc0 + j];
         const int u = A.uniq[A.doc0 + j];
-        for (int k = 0; k < u; ++k) {
-            const int t = A.rows[a + k];
-            best = fminf(best, A.D[(int64_t)t * A.V + w]);
+        if (w + 1 < A.V && (A.V & 1) == 0) {                                 // aligned pair loads
+            for (int k = 0; k < u; ++k)
+                best = __hmin2(best, *reinterpret_cast<const __half2 *>(A.D16 + (int64_t)A.rows[a + k] * A.V + w));
+        } else {
+            for (int k = 0; k < u; ++k) {
+                const __half *r = A.D16 + (int64_t)A.rows[a + k] * A.V;
+                best = __hmin2(best, __halves2half2(r[w], w + 1 < A.V ? r[w + 1] : inf));
+            }
         }
     }
     tile[y][x] = best;
     __syncthreads();
-    const int jw = j0 + x, ww = w0 + y;
-    if (jw < A.ndocs && ww < A.V) A.Z[(int64_t)ww * A.ldz + jw] = tile[x][y];
+    // transposed write: thread (x = document, y = word pair) stores two rows of Z
+    const int jw = j0 + x, ww = w0 + 2 * y;
+    if (jw < A.ndocs && ww < A.V) {
+        const __half2 v = tile[x][y];
+        A.Z[(int64_t)ww * A.ldz + jw] = __low2half(v);
+        if (ww + 1 < A.V) A.Z[(int64_t)(ww + 1) * A.ldz + jw] = __high2half(v);
+    }
 }
 
-// ---- LB tile: 32 query rows x 32 corpus columns per block -----------------------------------------
+// ---- LB tile: 128 query rows x 128 corpus columns per block ---------------------------------------
+// LB(i, j) = max(L1, L2),  L1 = sum over the tokens of A_i of weight * Z_B[row][j],  L2 = sum over the tokens of B_j of
+// weight * Z_A[row][i].  Every operand is rounded down and every FMA rounds toward zero (all terms are >= 0), so the
+// float32 result never exceeds the real-valued bound.  A warp task is one document and 128 documents of the other
+// side (4 per lane, one 8-byte load of Z per term): the document's (row, weight) list is warp-uniform, the Z loads are
+// coalesced, ~3 instructions per (pair, term).  L2 tasks run first and leave their tile transposed in shared memory.
 struct LbArgs {
-    // query side (set A), rows [i0, i0 + ni)
-    const int32_t *rowsA, *cntA; const int64_t *offA; const int32_t *uniqA; const int32_t *nvalA;
-    int64_t i0; int32_t ni;
-    // corpus side (set B)
-    const int32_t *rowsB, *cntB; const int64_t *offB; const int32_t *uniqB; const int32_t *nvalB;
+    const int2 *listA; const int64_t *offA; const int32_t *uniqA; const int32_t *nvalA;       // query side (set A)
+    int64_t i0; int32_t ni;                                                                   // rows [i0, i0 + ni)
+    const int2 *listB; const int64_t *offB; const int32_t *uniqB; const int32_t *nvalB;       // corpus side (set B)
     int32_t nB;
-    const float *ZB; int64_t ldzb;            // [V][nB]
-    const float *ZA; int64_t ldza;            // [V][ni] for this block of query rows
-    float *LB; int64_t ldlb;                  // [ni][nB]
+    const __half *ZB; int64_t ldzb;           // [V][ldzb], ldzb a multiple of 128
+    const __half *ZA; int64_t ldza;           // [V][ldza] for this block of query rows, ldza a multiple of 128
+    float *LB; int64_t ldlb;                  // [ni][ldlb]
 };
 
-__global__ void __launch_bounds__(1024)
-lb_tile_kernel(const __grid_constant__ LbArgs A)
+constexpr int kLbTile = 128;
+constexpr int kLbPitch = kLbTile + 1;
+
+__device__ __forceinline__ void lb_accumulate(const int2 *list, int u, const __half *Z, int64_t ldz, int col, float (&acc)[4])
 {
-    __shared__ double l2t[32][33];
-    const int x = threadIdx.x, y = threadIdx.y;
-    // query blocks vary fastest: the 32-column slice of Z_B (V x 128 B = 1.3 MB) of one corpus block stays
-    // L2-hot across all query blocks that reuse it
-    const int ib = blockIdx.x * 32, jb = blockIdx.y * 32;
-    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-    // L2(i, j): lanes along i (Z_A rows are contiguous in i), y = j
-    {
-        const int j = jb + y, i = ib + x;
-        double acc = kInf;
-        if (j < A.nB && i < A.ni) {
-            const int n = A.nvalB[j];
-            if (n > 0) {
-                acc = 0.0;
-                const int64_t a = A.offB[j];
-                const int u = A.uniqB[j];
-                const double inv = 1.0 / (double)n;              // bounds only: kLbMargin covers the rounding
-                for (int k = 0; k < u; ++k)
-                    acc += (double)A.cntB[a + k] * (double)A.ZA[(int64_t)A.rowsB[a + k] * A.ldza + i];
-                acc *= inv;
-            }
+    for (int k = 0; k < u; ++k) {
+        const int2 e = __ldg(list + k);                                      // warp-uniform
+        const float wgt = __int_as_float(e.y);
+        const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(Z + (int64_t)e.x * ldz + col));
+        const float2 z01 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 z23 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        acc[0] = __fmaf_rz(wgt, z01.x, acc[0]); acc[1] = __fmaf_rz(wgt, z01.y, acc[1]);
+        acc[2] = __fmaf_rz(wgt, z23.x, acc[2]); acc[3] = __fmaf_rz(wgt, z23.y, acc[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lb_tile16_kernel(const __grid_constant__ LbArgs A)
+{
+    extern __shared__ float l2t[];                                           // [128 corpus docs][kLbPitch] : L2(i, j) at [j][i]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // query blocks vary fastest: the column slice of Z_B of one corpus block stays L2-hot across the query blocks
+    const int ib = blockIdx.x * kLbTile, jb = blockIdx.y * kLbTile;
+    const float kInf = __int_as_float(0x7f800000);
+    // L2(i, j): one corpus document per task, lanes along i
+    for (int t = warp; t < kLbTile; t += 8) {
+        const int j = jb + t;
+        float acc[4] = { kInf, kInf, kInf, kInf };
+        if (j < A.nB && A.nvalB[j] > 0) {
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+            lb_accumulate(A.listB + A.offB[j], A.uniqB[j], A.ZA, A.ldza, ib + 4 * lane, acc);
         }
-        l2t[y][x] = acc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) l2t[t * kLbPitch + 4 * lane + c] = acc[c];
     }
     __syncthreads();
-    // L1(i, j): lanes along j, y = i
-    {
-        const int i = ib + y, j = jb + x;
-        if (i < A.ni && j < A.nB) {
-            double acc = kInf;
-            const int n = A.nvalA[A.i0 + i];
-            if (n > 0) {
-                acc = 0.0;
-                const int64_t a = A.offA[A.i0 + i];
-                const int u = A.uniqA[A.i0 + i];
-                const double inv = 1.0 / (double)n;
-                for (int k = 0; k < u; ++k)
-                    acc += (double)A.cntA[a + k] * (double)A.ZB[(int64_t)A.rowsA[a + k] * A.ldzb + j];
-                acc *= inv;
-            }
-            const double l2 = l2t[x][y];
-            double lb = acc > l2 ? acc : l2;            // inf if either side is empty
-            // round DOWN to float (and shave two ulps for the reciprocal weights) so that the stored
-            // bound never exceeds the exact one
-            float f = __double2float_rd(lb * (1.0 - 1e-12));
-            A.LB[(int64_t)i * A.ldlb + j] = f;
+    // L1(i, j): one query document per task, lanes along j
+    for (int t = warp; t < kLbTile; t += 8) {
+        const int i = ib + t;
+        if (i >= A.ni) break;
+        float acc[4] = { kInf, kInf, kInf, kInf };
+        if (A.nvalA[A.i0 + i] > 0) {
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+            lb_accumulate(A.listA + A.offA[A.i0 + i], A.uniqA[A.i0 + i], A.ZB, A.ldzb, jb + 4 * lane, acc);
         }
+        float4 o;
+        float *op = &o.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) op[c] = fmaxf(acc[c], l2t[(4 * lane + c) * kLbPitch + t]);     // inf if either side is empty
+        *reinterpret_cast<float4 *>(A.LB + (int64_t)i * A.ldlb + jb + 4 * lane) = o;              // columns >= nB are padding
     }
 }
 
@@ -313,7 +358,7 @@ scan_counts_kernel(const int32_t *counts, int32_t n, int64_t *offsets /* n + 1 *
 // >= 0 or +inf (NaN never occurs), so their bit patterns order like the values.
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(int32_t k, const int64_t *offsets, const int32_t *cj, const double *cd,
-                  int32_t *top_j, double *top_d, int32_t *kcur, float *thr /* k-th distance or +inf, rounded up */)
+                  int32_t *top_j, double *top_d, int32_t *kcur, float *thr /* k-th distance or +inf, rounded up */, float dmax)
 {
     extern __shared__ unsigned char sm_raw[];
     unsigned long long *okey = reinterpret_cast<unsigned long long *>(sm_raw);      // [k] merged keys
@@ -362,7 +407,7 @@ topk_merge_kernel(int32_t k, const int64_t *offsets, const int32_t *cj, const do
     if (threadIdx.x == 0) {
         kcur[r] = nout;
         float t = __int_as_float(0x7f800000);
-        if (nout == k) t = __double2float_ru(__longlong_as_double((long long)okey[k - 1]) + kLbMargin);
+        if (nout == k) t = __double2float_ru(__longlong_as_double((long long)okey[k - 1]) * (1.0 + kLbMarginRel) + kLbMarginRel * (double)dmax);
         thr[r] = t;
     }
 }

@@ -22,6 +22,8 @@ struct RwmdArgs {
     const int32_t *status;            // global pair indexing (p)
     double *lb, *l1, *l2;             // global pair indexing; l1/l2 may be null
     int32_t *argmin_rows, *argmin_cols;   // at the documents' own offsets (chunk-relative), may be null
+    int32_t am_abs;                   // != 0: the argmin arrays are indexed by absolute CSR offsets (device entry)
+    int32_t _pad;
 };
 
 __global__ void __launch_bounds__(256)
@@ -37,6 +39,7 @@ rwmd_pairs_kernel(const __grid_constant__ RwmdArgs A)
         int64_t a1, a2; int l;
         doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
         const int64_t o1 = slot_off(A.s1, tok1, q, a1), o2 = slot_off(A.s2, tok2, q, a2);
+        const int64_t m1 = A.am_abs ? a1 : o1, m2 = A.am_abs ? a2 : o2;
         const int st = A.status[p];
         if (st == 1) {
             if (lane == 0) { A.lb[p] = __longlong_as_double(0x7ff0000000000000LL); if (A.l1) A.l1[p] = A.lb[p]; if (A.l2) A.l2[p] = A.lb[p]; }
@@ -45,8 +48,8 @@ rwmd_pairs_kernel(const __grid_constant__ RwmdArgs A)
         if (st == 2) {
             if (lane == 0) {
                 A.lb[p] = 0.0; if (A.l1) A.l1[p] = 0.0; if (A.l2) A.l2[p] = 0.0;
-                if (A.argmin_rows) A.argmin_rows[o1] = 0;
-                if (A.argmin_cols) A.argmin_cols[o2] = 0;
+                if (A.argmin_rows) A.argmin_rows[m1] = 0;
+                if (A.argmin_cols) A.argmin_cols[m2] = 0;
             }
             continue;
         }
@@ -63,7 +66,7 @@ rwmd_pairs_kernel(const __grid_constant__ RwmdArgs A)
             float best = tile[(int64_t)i * u2]; int bj = 0;
             for (int j = 1; j < u2; ++j) { const float c = tile[(int64_t)i * u2 + j]; if (c < best) { best = c; bj = j; } }
             term[i] = __dmul_rn(__ddiv_rn((double)A.cnt1[o1 + i], (double)n1), (double)best);
-            if (A.argmin_rows) A.argmin_rows[o1 + i] = bj;
+            if (A.argmin_rows) A.argmin_rows[m1 + i] = bj;
         }
         __syncwarp();
         for (int i = 0; i < u1; ++i) s1 = __dadd_rn(s1, term[i]);
@@ -73,7 +76,7 @@ rwmd_pairs_kernel(const __grid_constant__ RwmdArgs A)
             float best = tile[j]; int bi = 0;
             for (int i = 1; i < u1; ++i) { const float c = tile[(int64_t)i * u2 + j]; if (c < best) { best = c; bi = i; } }
             term[j] = __dmul_rn(__ddiv_rn((double)A.cnt2[o2 + j], (double)n2), (double)best);
-            if (A.argmin_cols) A.argmin_cols[o2 + j] = bi;
+            if (A.argmin_cols) A.argmin_cols[m2 + j] = bi;
         }
         __syncwarp();
         for (int j = 0; j < u2; ++j) s2 = __dadd_rn(s2, term[j]);

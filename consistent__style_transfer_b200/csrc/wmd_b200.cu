@@ -117,10 +117,15 @@ struct wmd_engine {
     Workspace ws[2];
     // all-pairs mode (allpairs.cuh): V x V distance table (lazy) and a grow-only workspace
     float *dtab = nullptr;
+    __half *dtab16 = nullptr;                    // all-pairs mode: the table rounded down to half precision (bounds only)
     bool use_dtab = false;                       // pair path takes its costs from dtab (default policy: on when the table fits dtab_budget)
     float dmax = 0.f;
     size_t dtab_budget = 0;                      // bytes the table may take for the default policy to switch it on
     double dtab_build_ms = 0.0;                  // wall time of the one-off build
+    bool ids_are_rows = false;                   // this call's ids are table rows although a token map is installed (WMD_IDS_ARE_ROWS)
+    void *pin_in = nullptr, *pin_out = nullptr;  // wmd_pairs_submit / wmd_pairs_wait: handle-owned pinned staging
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
     cudaStream_t ap_stream = nullptr;
@@ -269,7 +274,7 @@ bool takes_fused(const wmd_engine *E, bool solve, bool rwmd, int mode);
 Vocab make_vocab(const wmd_engine *E)
 {
     Vocab v;
-    v.table = E->table; v.V = E->V; v.d = E->d; v.ld = E->ld; v.map = E->map; v.nmap = E->nmap; v.rank = E->rank;
+    v.table = E->table; v.V = E->V; v.d = E->d; v.ld = E->ld; v.map = E->ids_are_rows ? nullptr : E->map; v.nmap = E->nmap; v.rank = E->rank;
     return v;
 }
 
@@ -281,6 +286,7 @@ struct ChunkOut {
     int32_t *am1 = nullptr, *am2 = nullptr; // chunk-relative token offsets
     bool solve = true;
     int mode = WMD_MODE_PYEMD;
+    bool am_abs = false;                    // device entry: argmins at absolute CSR offsets
 };
 
 // K2: cost tiles of pairs [p0, p0 + Bc): the planned fast path for pairs that fit a stage, the
@@ -526,7 +532,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
         R.s1 = s1; R.s2 = s2; R.p0 = p0; R.npairs = Bc; R.Lp = ML;
         R.cnt1 = pw.cnt1; R.cnt2 = pw.cnt2; R.u12 = pw.u12;
         R.tiles = W.tiles.as<float>(); R.tile_stride = tile_stride; R.status = O.status;
-        R.lb = O.lb; R.l1 = O.l1; R.l2 = O.l2; R.argmin_rows = O.am1; R.argmin_cols = O.am2;
+        R.lb = O.lb; R.l1 = O.l1; R.l2 = O.l2; R.argmin_rows = O.am1; R.argmin_cols = O.am2; R.am_abs = O.am_abs ? 1 : 0; R._pad = 0;
         const int wpb = 8;
         const size_t smem = (size_t)wpb * ML * 8;
         const int grid = (int)std::min<int64_t>((Bc + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
@@ -590,6 +596,7 @@ int scan_offsets(const int64_t *off, int64_t n, int32_t &maxlen, const char *nam
         for (int64_t p = 0; p < n; ++p)
             if (off[p + 1] < off[p]) return fail(WMD_EINVAL, "%s offsets are not monotone at %lld", name, (long long)p);
     }
+    if (n > 0 && off[0] < 0) return fail(WMD_EINVAL, "%s offsets start below zero", name);
     if (mx > WMD_MAX_DOC_LEN) return fail(WMD_EINVAL, "%s holds a document of %lld tokens; the limit is %d", name, (long long)mx, WMD_MAX_DOC_LEN);
     maxlen = (int32_t)mx;
     return WMD_OK;
@@ -614,16 +621,12 @@ struct HostJob {
     bool rwmd = false, solve = true;
     int mode = WMD_MODE_PYEMD;
     double *lb = nullptr, *l1 = nullptr, *l2 = nullptr; int32_t *am1 = nullptr, *am2 = nullptr;
+    bool out_on_device = false;             // out / status are DEVICE arrays (wmd_pairs_host_in_dev_out)
 };
 
-int run_host_job(wmd_engine *E, const HostJob &J)
+int enqueue_host_job(wmd_engine *E, const HostJob &J)
 {
-    const auto t_job0 = std::chrono::steady_clock::now();
     int rc;
-    if ((rc = set_device(E))) return rc;
-    if (J.npairs < 0 || (J.npairs > 0 && (!J.off1 || !J.off2))) return fail(WMD_EINVAL, "null offsets");
-    if (J.npairs == 0) return WMD_OK;
-    if ((J.off1[J.npairs] > J.off1[0] && !J.ids1) || (J.off2[J.npairs] > J.off2[0] && !J.ids2)) return fail(WMD_EINVAL, "null ids");
     if (E->use_dtab && !E->dtab && (rc = ensure_dtab(E, E->streams[0]))) return rc;      // first call: build the word-distance table
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_fork, E->streams[0]));
@@ -635,10 +638,7 @@ int run_host_job(wmd_engine *E, const HostJob &J)
     for (int64_t c0 = 0; c0 < J.npairs; c0 += Bnext, slot = (slot ^ 1) & E->slot_mask) {
         const int64_t Btry = std::min<int64_t>(65536, J.npairs - c0);
         int32_t ml1, ml2;
-        if ((rc = scan_offsets(J.off1 + c0, Btry, ml1, "side 1")) || (rc = scan_offsets(J.off2 + c0, Btry, ml2, "side 2"))) {
-            cudaStreamSynchronize(E->streams[0]); cudaStreamSynchronize(E->streams[1]);
-            return rc;
-        }
+        if ((rc = scan_offsets(J.off1 + c0, Btry, ml1, "side 1")) || (rc = scan_offsets(J.off2 + c0, Btry, ml2, "side 2"))) return rc;
         const int32_t Bc = (int32_t)std::min<int64_t>(Btry, chunk_pairs(ml1, ml2, takes_fused(E, J.solve, J.rwmd, J.mode)));   // a shorter prefix keeps the same bounds
         Bnext = Bc;
         Workspace &W = E->ws[slot];
@@ -667,8 +667,9 @@ int run_host_job(wmd_engine *E, const HostJob &J)
             if (O.am2) CK(cudaMemsetAsync(W.am2.p, 0xff, (size_t)std::max<int64_t>(t2, 1) * 4, st));
         }
         if ((rc = run_chunk(E, W, st, s1, s2, 0, Bc, std::max<int64_t>(t1, 1), std::max<int64_t>(t2, 1), ml1, ml2, O))) return rc;
-        if (J.out) CK(cudaMemcpyAsync(J.out + c0, W.out.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
-        if (J.status) CK(cudaMemcpyAsync(J.status + c0, W.status.p, (size_t)Bc * 4, cudaMemcpyDeviceToHost, st));
+        const cudaMemcpyKind back = J.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (J.out) CK(cudaMemcpyAsync(J.out + c0, W.out.p, (size_t)Bc * 8, back, st));
+        if (J.status) CK(cudaMemcpyAsync(J.status + c0, W.status.p, (size_t)Bc * 4, back, st));
         if (J.rwmd) {
             if (J.lb) CK(cudaMemcpyAsync(J.lb + c0, W.lb.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
             if (J.l1) CK(cudaMemcpyAsync(J.l1 + c0, W.l1.p, (size_t)Bc * 8, cudaMemcpyDeviceToHost, st));
@@ -679,25 +680,61 @@ int run_host_job(wmd_engine *E, const HostJob &J)
         CK(cudaEventRecord(E->ev_slot[slot], st));
         E->slot_used[slot] = true;
     }
+    return WMD_OK;
+}
+
+// Waits for everything the engine's two streams hold.  Also the single exit of a failed host job: copies into the
+// caller's buffers that are already queued must have landed before the call reports its error.
+int drain_streams(wmd_engine *E)
+{
+    const cudaError_t e0 = cudaStreamSynchronize(E->streams[0]), e1 = cudaStreamSynchronize(E->streams[1]);
+    E->slot_used[0] = E->slot_used[1] = false;
+    if (e0 != cudaSuccess || e1 != cudaSuccess)
+        return fail(WMD_ECUDA, "stream synchronisation failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return WMD_OK;
+}
+
+int check_host_job(wmd_engine *E, const HostJob &J)
+{
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if (E->pending_pairs >= 0) return fail(WMD_EINVAL, "a submitted job is still in flight: call wmd_pairs_wait first");
+    if (J.npairs < 0 || (J.npairs > 0 && (!J.off1 || !J.off2))) return fail(WMD_EINVAL, "null offsets");
+    if (J.npairs > 0 && ((J.off1[J.npairs] > J.off1[0] && !J.ids1) || (J.off2[J.npairs] > J.off2[0] && !J.ids2))) return fail(WMD_EINVAL, "null ids");
+    return WMD_OK;
+}
+
+int run_host_job(wmd_engine *E, const HostJob &J)
+{
+    const auto t_job0 = std::chrono::steady_clock::now();
+    int rc;
+    if ((rc = check_host_job(E, J))) return rc;
+    if (J.npairs == 0) return WMD_OK;
+    rc = enqueue_host_job(E, J);
     const auto t_enq = std::chrono::steady_clock::now();
-    CK(cudaStreamSynchronize(E->streams[0]));
-    CK(cudaStreamSynchronize(E->streams[1]));
+    if (rc) {                                                    // keep the job's own message
+        const std::string msg = g_err;
+        drain_streams(E);
+        g_err = msg;
+        return rc;
+    }
+    if ((rc = drain_streams(E))) return rc;
     if (getenv("WMD_TRACE")) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "[wmd] host job %lld pairs: scan+enqueue %.3f ms, wait %.3f ms\n", (long long)J.npairs,
                 std::chrono::duration<double, std::milli>(t_enq - t_job0).count(), std::chrono::duration<double, std::milli>(t_end - t_enq).count());
     }
-    E->slot_used[0] = E->slot_used[1] = false;
     return WMD_OK;
 }
 
 // shared body of the device entries: fork from the caller's stream, chunk, join back; no host sync
 int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t total1, int64_t total2,
-                int32_t ml1, int32_t ml2, int64_t npairs, double *out, int32_t *status, cudaStream_t us, int mode = WMD_MODE_PYEMD)
+                int32_t ml1, int32_t ml2, int64_t npairs, const ChunkOut &O0, cudaStream_t us)
 {
     int rc;
     if ((rc = set_device(E))) return rc;
-    if (npairs < 0 || !out) return fail(WMD_EINVAL, "bad arguments");
+    if (E->pending_pairs >= 0) return fail(WMD_EINVAL, "a submitted job is still in flight: call wmd_pairs_wait first");
+    if (npairs < 0 || (O0.solve && !O0.out) || (O0.rwmd && !O0.lb)) return fail(WMD_EINVAL, "bad arguments");
     if (npairs == 0) return WMD_OK;
     if (ml1 < 0 || ml2 < 0 || ml1 > WMD_MAX_DOC_LEN || ml2 > WMD_MAX_DOC_LEN)
         return fail(WMD_EINVAL, "max_len must be within [0, %d]", WMD_MAX_DOC_LEN);
@@ -709,23 +746,24 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_join[0], 0));        // stats reset precedes both streams' kernels
-    const int64_t CH = chunk_pairs(ml1, ml2, takes_fused(E, true, false, mode));
+    const int64_t CH = chunk_pairs(ml1, ml2, takes_fused(E, O0.solve, O0.rwmd, O0.mode));
     int slot = 0;
     for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot = (slot ^ 1) & E->slot_mask) {
         const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - c0);
         Workspace &W = E->ws[slot];
-        if (!status) { if ((rc = W.status.ensure((size_t)Bc * 4))) return rc; }
-        ChunkOut O;
-        O.out = out; O.status = status; O.mode = mode;
-        int64_t p0 = c0;
-        DocSide a = s1, b = s2;
-        if (!status) {
-            // scratch status indexed from 0: shift so that status[p0 + q] lands in the scratch buffer
+        ChunkOut O = O0;
+        if (!O.status) {
+            // scratch status indexed from 0: shift so that status[c0 + q] lands in the scratch buffer
+            if ((rc = W.status.ensure((size_t)Bc * 4))) return rc;
             O.status = W.status.as<int32_t>() - c0;
+        }
+        if (!O.out) {                                                // bounds only: K1 still writes its early-outs somewhere
+            if ((rc = W.out.ensure((size_t)Bc * 8))) return rc;
+            O.out = W.out.as<double>() - c0;
         }
         const int64_t cap1 = std::max<int64_t>(1, std::min<int64_t>(total1, (int64_t)Bc * ml1));
         const int64_t cap2 = std::max<int64_t>(1, std::min<int64_t>(total2, (int64_t)Bc * ml2));
-        if ((rc = run_chunk(E, W, E->streams[slot], a, b, p0, Bc, cap1, cap2, ml1, ml2, O))) return rc;
+        if ((rc = run_chunk(E, W, E->streams[slot], s1, s2, c0, Bc, cap1, cap2, ml1, ml2, O))) return rc;
     }
     CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
     CK(cudaEventRecord(E->ev_join[1], E->streams[1]));
@@ -734,13 +772,22 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     return WMD_OK;
 }
 
+int run_dev_pairs(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t total1, int64_t total2, int32_t ml1, int32_t ml2,
+                  int64_t npairs, double *out, int32_t *status, cudaStream_t us, int mode = WMD_MODE_PYEMD)
+{
+    if (!out && npairs > 0) return fail(WMD_EINVAL, "out is null");
+    ChunkOut O;
+    O.out = out; O.status = status; O.mode = mode;
+    return run_dev_job(E, s1, s2, total1, total2, ml1, ml2, npairs, O, us);
+}
+
 // ------------------------------------------------------------------------------------------------
 // all-pairs mode
 // ------------------------------------------------------------------------------------------------
 enum {
     AP_IDSA, AP_OFFA, AP_IDSB, AP_OFFB, AP_ROWSA, AP_CNTA, AP_UNIQA, AP_NVALA, AP_ROWSB, AP_CNTB, AP_UNIQB, AP_NVALB,
     AP_ZB, AP_ZA, AP_LB, AP_KTH, AP_THR, AP_COUNTS, AP_OFFS, AP_CI, AP_CJ, AP_CD, AP_CST, AP_TOPJ, AP_TOPD, AP_KCUR,
-    AP_BIJ, AP_COUNT_
+    AP_BIJ, AP_LISTA, AP_LISTB, AP_COUNT_
 };
 static_assert(AP_COUNT_ <= 32, "wmd_engine::ap too small");
 
@@ -801,13 +848,27 @@ int ensure_dtab(wmd_engine *E, cudaStream_t st)
     return WMD_OK;
 }
 
-// rows / counts / uniq / nval of ndocs documents already on the device
+// all-pairs mode: the half-precision copy of the table the bound kernels read
+int ensure_dtab16(wmd_engine *E, cudaStream_t st)
+{
+    if (E->dtab16) return WMD_OK;
+    const int64_t n = (int64_t)E->V * E->V;
+    __half *p = nullptr;
+    if (cudaMalloc(&p, (size_t)n * 2) != cudaSuccess) return fail(WMD_ENOMEM, "cudaMalloc(half-precision distance table) failed");
+    dtab_to_half_kernel<<<E->sm_count * 8, 256, 0, st>>>(E->dtab, n, p);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(p); return fail(WMD_ECUDA, "dtab_to_half_kernel failed"); }
+    E->dtab16 = p;
+    return WMD_OK;
+}
+
+// rows / counts / uniq / nval and the packed (row, weight) lists of ndocs documents already on the device
 int ap_nbow(wmd_engine *E, cudaStream_t st, const int32_t *ids_dev, const int64_t *off_dev, int64_t ndocs, int32_t ml, int64_t total,
-            DevBuf &rows, DevBuf &cnt, DevBuf &uniq, DevBuf &nval)
+            DevBuf &rows, DevBuf &cnt, DevBuf &uniq, DevBuf &nval, DevBuf &lists)
 {
     int rc;
     const size_t tb = (size_t)std::max<int64_t>(total, 1);
-    if ((rc = rows.ensure(tb * 4)) || (rc = cnt.ensure(tb * 4)) || (rc = uniq.ensure((size_t)ndocs * 4)) || (rc = nval.ensure((size_t)ndocs * 4)))
+    if ((rc = rows.ensure(tb * 4)) || (rc = cnt.ensure(tb * 4)) || (rc = uniq.ensure((size_t)ndocs * 4)) || (rc = nval.ensure((size_t)ndocs * 4)) ||
+        (rc = lists.ensure(tb * 8)))
         return rc;
     DocSide s{};
     s.ids = ids_dev; s.off = off_dev;
@@ -820,15 +881,28 @@ int ap_nbow(wmd_engine *E, cudaStream_t st, const int32_t *ids_dev, const int64_
     nbow_docs_kernel<<<grid, wpb * 32, smem, st>>>(s, make_vocab(E), (int32_t)ndocs, Lp, rows.as<int32_t>(), cnt.as<int32_t>(), nullptr,
                                                   uniq.as<int32_t>(), nval.as<int32_t>());
     CK(cudaGetLastError());
+    pack_lists_kernel<<<(unsigned)((ndocs + 255) / 256), 256, 0, st>>>(rows.as<int32_t>(), cnt.as<int32_t>(), off_dev, uniq.as<int32_t>(),
+                                                                        nval.as<int32_t>(), ndocs, lists.as<int2>());
+    CK(cudaGetLastError());
     return WMD_OK;
 }
 
-struct ApTimer {
-    cudaEvent_t a = nullptr, b = nullptr; cudaStream_t st;
-    explicit ApTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    ~ApTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
-    void start() { cudaEventRecord(a, st); }
-    double stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float t = 0.f; cudaEventElapsedTime(&t, a, b); return t; }
+// Phase timer of the all-pairs entry: events are only recorded while the job is queued and read once at the end, so
+// timing never stalls the stream (the previous version synchronised at every phase boundary).
+struct ApPhases {
+    cudaStream_t st;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> phase;                                    // phase of the interval that ENDS at ev[i] (ev[0]: start)
+    explicit ApPhases(cudaStream_t s) : st(s) { mark(-1); }
+    ~ApPhases() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    void mark(int ph) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); phase.push_back(ph); }
+    void collect(double *ms, int n)                            // call after the stream has been synchronised
+    {
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float t = 0.f;
+            if (phase[i] >= 0 && phase[i] < n && cudaEventElapsedTime(&t, ev[i - 1], ev[i]) == cudaSuccess) ms[phase[i]] += t;
+        }
+    }
 };
 
 // exact WMD of the candidate pairs (ci[p] in A, cj[p] in B) -> cd[p]
@@ -839,20 +913,22 @@ int ap_exact(wmd_engine *E, cudaStream_t st, const int32_t *idsA, const int64_t 
     DocSide s1{}, s2{};
     s1.ids = idsA; s1.off = offA; s1.sel = ci; s1.slot = std::max(mlA, 1);
     s2.ids = idsB; s2.off = offB; s2.sel = cj; s2.slot = std::max(mlB, 1);
-    // all-pairs mode owns the word-distance table (its bounds are built from it), so the candidates' cost tiles are
-    // gathered from it instead of recomputed: the same values, and the exact rounds take half the time
+    // all-pairs mode owns the word-distance table (its bounds are built from it), so the candidates go through the
+    // table-mode path -- the fused warp-per-pair kernel -- whatever the handle's policy for the pair entries is
     const bool prev = E->use_dtab;
     E->use_dtab = E->dtab != nullptr;
-    const int rc = run_dev_job(E, s1, s2, n * (int64_t)std::max(mlA, 1), n * (int64_t)std::max(mlB, 1), mlA, mlB, n, cd, cst, st);
+    const int rc = run_dev_pairs(E, s1, s2, n * (int64_t)std::max(mlA, 1), n * (int64_t)std::max(mlB, 1), mlA, mlB, n, cd, cst, st);
     E->use_dtab = prev;
     return rc;
 }
 
 int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_t nA, const int32_t *idsB, const int64_t *offB, int64_t nB,
-                 int32_t k, int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist, int64_t *stats, double *ms)
+                 int32_t k, int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist, bool out_on_device,
+                 int64_t *stats, double *ms)
 {
     int rc;
     if ((rc = set_device(E))) return rc;
+    if (E->pending_pairs >= 0) return fail(WMD_EINVAL, "a submitted job is still in flight: call wmd_pairs_wait first");
     if (nA < 0 || nB < 0 || k <= 0 || row_begin < 0 || row_end > nA || row_begin > row_end) return fail(WMD_EINVAL, "bad all-pairs arguments");
     if (nA > 0x7fffffff || nB > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
     if (k > nB) return fail(WMD_EINVAL, "k = %d exceeds the %lld documents of set B", k, (long long)nB);
@@ -860,21 +936,24 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
     const int64_t nR = row_end - row_begin;
     if (nR == 0) return WMD_OK;
     if (!offA || !offB || !out_idx || !out_dist) return fail(WMD_EINVAL, "null argument");
+    E->ids_are_rows = false;
     int32_t mlA = 0, mlB = 0;
     if ((rc = scan_offsets(offA + row_begin, nR, mlA, "set A"))) return rc;
     if ((rc = scan_offsets(offB, nB, mlB, "set B"))) return rc;
     cudaStream_t st = E->ap_stream;
     DevBuf *B = E->ap;
-    ApTimer tm(st);
     double ms_local[4] = { 0, 0, 0, 0 };                       // distance table, corpus index (Z_B), bounds + selection, exact solves
     int64_t st_local[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };          // lb pairs, round-1 solves, round-2 solves, query blocks
 
-    tm.start();
-    if ((rc = ensure_dtab(E, st))) return rc;
-    ms_local[0] = tm.stop();
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool fresh = !E->dtab || !E->dtab16;
+        if ((rc = ensure_dtab(E, st)) || (rc = ensure_dtab16(E, st))) return rc;
+        if (fresh) ms_local[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    ApPhases tm(st);
 
     // ---- documents to the device; nBOW of both sets ------------------------------------------------
-    tm.start();
     const int64_t baseA = offA[row_begin], totA = offA[row_end] - baseA, baseB = offB[0], totB = offB[nB] - baseB;
     if ((totA > 0 && !idsA) || (totB > 0 && !idsB)) return fail(WMD_EINVAL, "null ids");
     if ((rc = B[AP_IDSA].ensure((size_t)std::max<int64_t>(totA, 1) * 4)) || (rc = B[AP_OFFA].ensure((size_t)(nR + 1) * 8)) ||
@@ -887,51 +966,51 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
     // offsets stay absolute; rebase the id pointers instead
     const int32_t *dIdsA = B[AP_IDSA].as<int32_t>() - baseA, *dIdsB = B[AP_IDSB].as<int32_t>() - baseB;
     const int64_t *dOffA = B[AP_OFFA].as<int64_t>(), *dOffB = B[AP_OFFB].as<int64_t>();
-    if ((rc = ap_nbow(E, st, dIdsA, dOffA, nR, mlA, totA + baseA, B[AP_ROWSA], B[AP_CNTA], B[AP_UNIQA], B[AP_NVALA]))) return rc;
-    if ((rc = ap_nbow(E, st, dIdsB, dOffB, nB, mlB, totB + baseB, B[AP_ROWSB], B[AP_CNTB], B[AP_UNIQB], B[AP_NVALB]))) return rc;
+    if ((rc = ap_nbow(E, st, dIdsA, dOffA, nR, mlA, totA + baseA, B[AP_ROWSA], B[AP_CNTA], B[AP_UNIQA], B[AP_NVALA], B[AP_LISTA]))) return rc;
+    if ((rc = ap_nbow(E, st, dIdsB, dOffB, nB, mlB, totB + baseB, B[AP_ROWSB], B[AP_CNTB], B[AP_UNIQB], B[AP_NVALB], B[AP_LISTB]))) return rc;
     // ---- Z_B[w][j] ----------------------------------------------------------------------------------
-    const int64_t ldzb = (nB + 31) & ~31ll;
-    if ((rc = B[AP_ZB].ensure((size_t)E->V * ldzb * 4))) return rc;
+    const int64_t ldzb = (nB + kLbTile - 1) / kLbTile * kLbTile;
+    if ((rc = B[AP_ZB].ensure((size_t)E->V * ldzb * 2))) return rc;
     {
         ZArgs Z;
-        Z.D = E->dtab; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSB].as<int32_t>(); Z.off = dOffB; Z.uniq = B[AP_UNIQB].as<int32_t>();
-        Z.doc0 = 0; Z.ndocs = (int32_t)nB; Z.Z = B[AP_ZB].as<float>(); Z.ldz = ldzb;
-        dim3 grid((unsigned)((nB + 31) / 32), (unsigned)((E->V + 31) / 32));
-        z_build_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
+        Z.D16 = E->dtab16; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSB].as<int32_t>(); Z.off = dOffB; Z.uniq = B[AP_UNIQB].as<int32_t>();
+        Z.doc0 = 0; Z.ndocs = (int32_t)nB; Z.Z = B[AP_ZB].as<__half>(); Z.ldz = ldzb;
+        dim3 grid((unsigned)((nB + 31) / 32), (unsigned)((E->V + 63) / 64));
+        z_build16_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
         CK(cudaGetLastError());
     }
-    ms_local[1] = tm.stop();
+    tm.mark(1);
 
     // ---- query blocks ---------------------------------------------------------------------------------
-    int64_t IB = std::min<int64_t>(nR, std::max<int64_t>(32, (int64_t)(1ll << 29) / std::max<int64_t>(nB, 1)));
+    int64_t IB = std::min<int64_t>((nR + kLbTile - 1) / kLbTile * kLbTile, std::max<int64_t>(kLbTile, (int64_t)(1ll << 29) / std::max<int64_t>(ldzb, 1) / kLbTile * kLbTile));
     IB = std::min<int64_t>(IB, 4096);
-    const int64_t ldza = (IB + 31) & ~31ll, ldlb = ldzb;
-    if ((rc = B[AP_ZA].ensure((size_t)E->V * ldza * 4)) || (rc = B[AP_LB].ensure((size_t)IB * ldlb * 4)) || (rc = B[AP_KTH].ensure((size_t)IB * 4)) ||
+    const int64_t ldza = IB, ldlb = ldzb;
+    if ((rc = B[AP_ZA].ensure((size_t)E->V * ldza * 2)) || (rc = B[AP_LB].ensure((size_t)IB * ldlb * 4)) || (rc = B[AP_KTH].ensure((size_t)IB * 4)) ||
         (rc = B[AP_THR].ensure((size_t)IB * 4)) || (rc = B[AP_COUNTS].ensure((size_t)IB * 4)) || (rc = B[AP_OFFS].ensure((size_t)(IB + 1) * 8)) ||
         (rc = B[AP_TOPJ].ensure((size_t)IB * k * 4)) || (rc = B[AP_TOPD].ensure((size_t)IB * k * 8)) || (rc = B[AP_KCUR].ensure((size_t)IB * 4)))
         return rc;
+    const size_t lb_smem = (size_t)kLbTile * kLbPitch * 4;
+    CK(cudaFuncSetAttribute(lb_tile16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem));
+    const cudaMemcpyKind back = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     for (int64_t i0 = 0; i0 < nR; i0 += IB) {
         const int32_t ni = (int32_t)std::min<int64_t>(IB, nR - i0);
         st_local[3] += 1;
-        tm.start();
         {
             ZArgs Z;
-            Z.D = E->dtab; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSA].as<int32_t>(); Z.off = dOffA; Z.uniq = B[AP_UNIQA].as<int32_t>();
-            Z.doc0 = i0; Z.ndocs = ni; Z.Z = B[AP_ZA].as<float>(); Z.ldz = ldza;
-            // rows of set A live at their absolute CSR offsets minus baseA: shift the pointer like the ids
-            Z.rows = B[AP_ROWSA].as<int32_t>();
-            dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((E->V + 31) / 32));
-            z_build_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
+            Z.D16 = E->dtab16; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSA].as<int32_t>(); Z.off = dOffA; Z.uniq = B[AP_UNIQA].as<int32_t>();
+            Z.doc0 = i0; Z.ndocs = ni; Z.Z = B[AP_ZA].as<__half>(); Z.ldz = ldza;
+            dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((E->V + 63) / 64));
+            z_build16_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
             CK(cudaGetLastError());
             LbArgs L;
-            L.rowsA = B[AP_ROWSA].as<int32_t>(); L.cntA = B[AP_CNTA].as<int32_t>(); L.offA = dOffA; L.uniqA = B[AP_UNIQA].as<int32_t>();
-            L.nvalA = B[AP_NVALA].as<int32_t>(); L.i0 = i0; L.ni = ni;
-            L.rowsB = B[AP_ROWSB].as<int32_t>(); L.cntB = B[AP_CNTB].as<int32_t>(); L.offB = dOffB; L.uniqB = B[AP_UNIQB].as<int32_t>();
-            L.nvalB = B[AP_NVALB].as<int32_t>(); L.nB = (int32_t)nB;
-            L.ZB = B[AP_ZB].as<float>(); L.ldzb = ldzb; L.ZA = B[AP_ZA].as<float>(); L.ldza = ldza;
+            L.listA = B[AP_LISTA].as<int2>(); L.offA = dOffA; L.uniqA = B[AP_UNIQA].as<int32_t>(); L.nvalA = B[AP_NVALA].as<int32_t>();
+            L.i0 = i0; L.ni = ni;
+            L.listB = B[AP_LISTB].as<int2>(); L.offB = dOffB; L.uniqB = B[AP_UNIQB].as<int32_t>(); L.nvalB = B[AP_NVALB].as<int32_t>();
+            L.nB = (int32_t)nB;
+            L.ZB = B[AP_ZB].as<__half>(); L.ldzb = ldzb; L.ZA = B[AP_ZA].as<__half>(); L.ldza = ldza;
             L.LB = B[AP_LB].as<float>(); L.ldlb = ldlb;
-            dim3 g2((unsigned)((ni + 31) / 32), (unsigned)((nB + 31) / 32));
-            lb_tile_kernel<<<g2, dim3(32, 32), 0, st>>>(L);
+            dim3 g2((unsigned)((ni + kLbTile - 1) / kLbTile), (unsigned)(ldzb / kLbTile));
+            lb_tile16_kernel<<<g2, 256, lb_smem, st>>>(L);
             CK(cudaGetLastError());
             st_local[0] += (int64_t)ni * nB;
         }
@@ -948,9 +1027,8 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             CK(cudaGetLastError());
             int64_t ncand = 0;
             CK(cudaMemcpyAsync(&ncand, B[AP_OFFS].as<int64_t>() + ni, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (round == 0) ms_local[2] += tm.stop(); else ms_local[2] += tm.stop();
-            tm.start();
+            tm.mark(2);
+            CK(cudaStreamSynchronize(st));                     // the one host round trip per round: the candidate count sizes the exact job
             if (ncand > 0) {
                 if ((rc = B[AP_CI].ensure((size_t)ncand * 4)) || (rc = B[AP_CJ].ensure((size_t)ncand * 4)) || (rc = B[AP_CD].ensure((size_t)ncand * 8)) ||
                     (rc = B[AP_CST].ensure((size_t)ncand * 4)))
@@ -964,20 +1042,49 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             }
             topk_merge_kernel<<<ni, 256, (size_t)k * 12, st>>>(k, B[AP_OFFS].as<int64_t>(), B[AP_CJ].as<int32_t>(), B[AP_CD].as<double>(),
                                                              B[AP_TOPJ].as<int32_t>(), B[AP_TOPD].as<double>(), B[AP_KCUR].as<int32_t>(),
-                                                             B[AP_THR].as<float>());
+                                                             B[AP_THR].as<float>(), E->dmax);
             CK(cudaGetLastError());
             st_local[1 + round] += ncand;
-            ms_local[3] += tm.stop();
-            tm.start();
+            tm.mark(3);
         }
-        CK(cudaMemcpyAsync(out_idx + i0 * k, B[AP_TOPJ].p, (size_t)ni * k * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(out_dist + i0 * k, B[AP_TOPD].p, (size_t)ni * k * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        ms_local[2] += tm.stop();
+        CK(cudaMemcpyAsync(out_idx + i0 * k, B[AP_TOPJ].p, (size_t)ni * k * 4, back, st));
+        CK(cudaMemcpyAsync(out_dist + i0 * k, B[AP_TOPD].p, (size_t)ni * k * 8, back, st));
+        tm.mark(2);
     }
+    CK(cudaStreamSynchronize(st));
+    tm.collect(ms_local, 4);
     if (stats) for (int i = 0; i < 8; ++i) stats[i] = st_local[i];
     if (ms) for (int i = 0; i < 4; ++i) ms[i] = ms_local[i];
     return WMD_OK;
+}
+
+// mode argument of the pair entries: WMD_MODE_* in the low byte, WMD_IDS_ARE_ROWS as a flag
+int parse_mode(wmd_engine *E, int32_t mode, int &base)
+{
+    base = mode & 0xff;
+    if ((mode & ~(0xff | WMD_IDS_ARE_ROWS)) || (base != WMD_MODE_PYEMD && base != WMD_MODE_EXACT)) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    E->ids_are_rows = (mode & WMD_IDS_ARE_ROWS) != 0;
+    return WMD_OK;
+}
+
+int ensure_pinned(void *&p, size_t &cap, size_t bytes)
+{
+    if (bytes <= cap) return WMD_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 2 + 4096;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return fail(WMD_ENOMEM, "cudaHostAlloc(%zu) failed", want); }
+    cap = want;
+    return WMD_OK;
+}
+
+size_t workspace_resident(const Workspace &W)
+{
+    const DevBuf *all[] = { &W.ids1, &W.ids2, &W.off1, &W.off2, &W.rows1, &W.cnt1, &W.ip1, &W.rows2, &W.cnt2, &W.ip2, &W.u12, &W.meta, &W.pqn,
+                            &W.extra, &W.maxc, &W.tiles, &W.out, &W.status, &W.scratch, &W.plan, &W.wt1, &W.wt2, &W.lb, &W.l1, &W.l2, &W.am1, &W.am2,
+                            &W.counters, &W.biglist };
+    size_t t = 0;
+    for (const DevBuf *b : all) t += b->cap;
+    return t;
 }
 
 }  // namespace
@@ -1067,12 +1174,15 @@ int wmd_destroy(wmd_handle E)
     }
     if (E->ev_fork) cudaEventDestroy(E->ev_fork);
     if (E->dtab) cudaFree(E->dtab);
+    if (E->dtab16) cudaFree(E->dtab16);
     for (auto &b : E->ap) b.release();
     if (E->ap_stream) cudaStreamDestroy(E->ap_stream);
     if (E->table) cudaFree(E->table);
     if (E->map) cudaFree(E->map);
     if (E->rank) cudaFree(E->rank);
     if (E->stats) cudaFree(E->stats);
+    if (E->pin_in) cudaFreeHost(E->pin_in);
+    if (E->pin_out) cudaFreeHost(E->pin_out);
     delete E;
     return WMD_OK;
 }
@@ -1125,11 +1235,113 @@ int wmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, const
                    int64_t npairs, int32_t mode, double *out, int32_t *status)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    int base, rc;
+    if ((rc = parse_mode(E, mode, base))) return rc;
     if (!out && npairs > 0) return fail(WMD_EINVAL, "out is null");
     HostJob J{ ids1, off1, ids2, off2, npairs, out, status };
-    J.mode = mode;
+    J.mode = base;
     return run_host_job(E, J);
+}
+
+int wmd_pairs_host_in_dev_out(wmd_handle E, const int32_t *ids1, const int64_t *off1, const int32_t *ids2, const int64_t *off2,
+                              int64_t npairs, int32_t mode, double *out_dev, int32_t *status_dev)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    int base, rc;
+    if ((rc = parse_mode(E, mode, base))) return rc;
+    if (!out_dev && npairs > 0) return fail(WMD_EINVAL, "out is null");
+    HostJob J{ ids1, off1, ids2, off2, npairs, out_dev, status_dev };
+    J.mode = base; J.out_on_device = true;
+    return run_host_job(E, J);
+}
+
+/* Asynchronous form of wmd_pairs_host for batches of the in-loop caller's size (src/loader.py:60): the documents are
+ * staged into pinned memory the handle owns, copies and kernels are queued on the handle's streams and the call
+ * returns; wmd_pairs_wait blocks until the scores are back and hands them over. */
+int wmd_pairs_submit(wmd_handle E, const int32_t *ids1, const int64_t *off1, const int32_t *ids2, const int64_t *off2,
+                     int64_t npairs, int32_t mode)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    int base, rc;
+    if ((rc = parse_mode(E, mode, base))) return rc;
+    HostJob J{ ids1, off1, ids2, off2, npairs, nullptr, nullptr };
+    J.mode = base;
+    if ((rc = check_host_job(E, J))) return rc;
+    if (npairs == 0) { E->pending_pairs = 0; return WMD_OK; }
+    const int64_t b1 = off1[0], b2 = off2[0], t1 = off1[npairs] - b1, t2 = off2[npairs] - b2;
+    if (b1 < 0 || b2 < 0 || t1 < 0 || t2 < 0) return fail(WMD_EINVAL, "bad offsets");
+    const size_t n_off = (size_t)(npairs + 1) * 8, n1 = (size_t)t1 * 4, n2 = (size_t)t2 * 4;
+    const size_t in_bytes = 2 * n_off + ((n1 + 7) & ~(size_t)7) + n2 + 16;
+    if ((rc = ensure_pinned(E->pin_in, E->pin_in_cap, in_bytes)) || (rc = ensure_pinned(E->pin_out, E->pin_out_cap, (size_t)npairs * 12 + 16))) return rc;
+    // pinned layout: off1 | off2 | ids1 | ids2  (offsets rebased to zero)
+    int64_t *po1 = static_cast<int64_t *>(E->pin_in), *po2 = po1 + npairs + 1;
+    int32_t *pi1 = reinterpret_cast<int32_t *>(po2 + npairs + 1);
+    int32_t *pi2 = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(pi1) + ((n1 + 7) & ~(size_t)7));
+    for (int64_t p = 0; p <= npairs; ++p) { po1[p] = off1[p] - b1; po2[p] = off2[p] - b2; }
+    if (t1) memcpy(pi1, ids1 + b1, n1);
+    if (t2) memcpy(pi2, ids2 + b2, n2);
+    J.ids1 = pi1; J.off1 = po1; J.ids2 = pi2; J.off2 = po2;
+    J.out = static_cast<double *>(E->pin_out);
+    J.status = reinterpret_cast<int32_t *>(J.out + npairs);
+    if ((rc = enqueue_host_job(E, J))) {
+        const std::string msg = g_err;
+        drain_streams(E);
+        g_err = msg;
+        return rc;
+    }
+    E->pending_pairs = npairs;
+    return WMD_OK;
+}
+
+int wmd_pairs_wait(wmd_handle E, double *out, int32_t *status)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (E->pending_pairs < 0) return fail(WMD_EINVAL, "no submitted job to wait for");
+    const int64_t n = E->pending_pairs;
+    E->pending_pairs = -1;
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    if (n == 0) return WMD_OK;
+    if (!out) { drain_streams(E); return fail(WMD_EINVAL, "out is null"); }
+    if ((rc = drain_streams(E))) return rc;
+    const double *po = static_cast<const double *>(E->pin_out);
+    memcpy(out, po, (size_t)n * 8);
+    if (status) memcpy(status, po + n, (size_t)n * 4);
+    return WMD_OK;
+}
+
+int wmd_workspace_bytes(wmd_handle E, int64_t npairs, int32_t max_len1, int32_t max_len2, int64_t *estimate, int64_t *resident)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (npairs < 0 || max_len1 < 0 || max_len2 < 0 || max_len1 > WMD_MAX_DOC_LEN || max_len2 > WMD_MAX_DOC_LEN) return fail(WMD_EINVAL, "bad sizes");
+    const int ml1 = std::max(max_len1, 1), ml2 = std::max(max_len2, 1), ML = std::max(ml1, ml2);
+    const bool table = E->use_dtab;
+    const size_t fixed = (size_t)E->V * E->ld * 4 + (size_t)E->nmap * 4 + (E->rank ? (size_t)E->V * 4 : 0) +
+                         (table ? (size_t)E->V * E->V * 4 : 0);
+    if (estimate) {
+        const int64_t Bc = std::min<int64_t>(npairs, chunk_pairs(ml1, ml2, table));
+        const int slots = npairs > Bc ? 2 : 1;
+        size_t per = (size_t)Bc * (2 * 8 + 8 + 4 + 4);                                   // offsets, out, status, biglist
+        per += (size_t)Bc * (size_t)(ml1 + ml2) * 4;                                     // staged ids (upper bound)
+        const bool general = !table || ML >= 32;
+        if (general) {
+            per += (size_t)Bc * (size_t)(ml1 + ml2) * 12 + (size_t)Bc * 28;              // rows / counts / masses, per-pair records
+            if (!table) {
+                per += (size_t)Bc * ml1 * ml2 * 4;                                       // cost tiles
+                per += (size_t)plan_stage_bound(Bc, ml1, ml2, Bc * (int64_t)ml1, Bc * (int64_t)ml2, std::max(E->fast_R, 8), kStageTilesMax) * sizeof(StageRec);
+            }
+            if (ML >= 64) per += (size_t)E->sm_count * 12 * 2 * (size_t)std::min(ML, kMaxDocLen) * (std::min(ML, kMaxDocLen) + 2) * 4;   // class C scratch
+            else if (ML >= 32) per += (size_t)E->sm_count * 32 * (size_t)64 * 65 * 4;    // class B flow scratch
+        }
+        *estimate = (int64_t)(fixed + (size_t)slots * per);
+    }
+    if (resident) {
+        size_t r = (size_t)E->V * E->ld * 4 + (size_t)E->nmap * 4 + (E->rank ? (size_t)E->V * 4 : 0) + (E->dtab ? (size_t)E->V * E->V * 4 : 0);
+        r += workspace_resident(E->ws[0]) + workspace_resident(E->ws[1]);
+        for (const DevBuf &b : E->ap) r += b.cap;
+        *resident = (int64_t)r;
+    }
+    return WMD_OK;
 }
 
 int wmd_rwmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, const int32_t *ids2, const int64_t *off2,
@@ -1138,6 +1350,7 @@ int wmd_rwmd_pairs_host(wmd_handle E, const int32_t *ids1, const int64_t *off1, 
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
     if (!lb && npairs > 0) return fail(WMD_EINVAL, "lb is null");
+    E->ids_are_rows = false;
     HostJob J{ ids1, off1, ids2, off2, npairs, nullptr, status };
     J.rwmd = true; J.solve = false; J.lb = lb; J.l1 = l1; J.l2 = l2; J.am1 = argmin_rows; J.am2 = argmin_cols;
     return run_host_job(E, J);
@@ -1148,24 +1361,66 @@ int wmd_pairs_dev(wmd_handle E, const int32_t *ids1, const int64_t *off1, int64_
                   int64_t npairs, int32_t mode, double *out, int32_t *status, void *stream)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    int base, rc;
+    if ((rc = parse_mode(E, mode, base))) return rc;
     if (npairs > 0 && (!off1 || !off2)) return fail(WMD_EINVAL, "null offsets");
     DocSide s1{}, s2{};
     s1.ids = ids1; s1.off = off1; s2.ids = ids2; s2.off = off2;
-    return run_dev_job(E, s1, s2, total1, total2, max_len1, max_len2, npairs, out, status, (cudaStream_t)stream, mode);
+    return run_dev_pairs(E, s1, s2, total1, total2, max_len1, max_len2, npairs, out, status, (cudaStream_t)stream, base);
+}
+
+int wmd_rwmd_pairs_dev(wmd_handle E, const int32_t *ids1, const int64_t *off1, int64_t total1, int32_t max_len1,
+                       const int32_t *ids2, const int64_t *off2, int64_t total2, int32_t max_len2, int64_t npairs,
+                       double *lb, double *l1, double *l2, int32_t *argmin_rows, int32_t *argmin_cols, int32_t *status, void *stream)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (npairs > 0 && (!off1 || !off2 || !lb)) return fail(WMD_EINVAL, "null argument");
+    E->ids_are_rows = false;
+    DocSide s1{}, s2{};
+    s1.ids = ids1; s1.off = off1; s2.ids = ids2; s2.off = off2;
+    ChunkOut O;
+    O.out = nullptr; O.status = status; O.solve = false; O.rwmd = true; O.am_abs = true;
+    O.lb = lb; O.l1 = l1; O.l2 = l2; O.am1 = argmin_rows; O.am2 = argmin_cols;
+    return run_dev_job(E, s1, s2, total1, total2, max_len1, max_len2, npairs, O, (cudaStream_t)stream);
+}
+
+int wmd_nbow_dev(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t ndocs, int32_t max_len,
+                 int32_t *rows, int32_t *counts, double *weights, int32_t *uniq, void *stream)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (ndocs < 0 || (ndocs > 0 && (!off || !rows || !counts || !uniq))) return fail(WMD_EINVAL, "null argument");
+    if (max_len < 0 || max_len > WMD_MAX_DOC_LEN) return fail(WMD_EINVAL, "max_len must be within [0, %d]", WMD_MAX_DOC_LEN);
+    if (ndocs == 0) return WMD_OK;
+    if (ndocs > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    E->ids_are_rows = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    DocSide s{};
+    s.ids = ids; s.off = off;
+    const int Lp = std::max(max_len, 1);
+    const int wpb = Lp <= 64 ? 8 : 4;
+    const size_t smem = nbow_smem_per_warp(Lp) * wpb;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(nbow_docs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>((ndocs + wpb - 1) / wpb, (int64_t)E->sm_count * 8);
+    Prof pr(E, WMD_K_NBOW, st);
+    nbow_docs_kernel<<<grid, wpb * 32, smem, st>>>(s, make_vocab(E), (int32_t)ndocs, Lp, rows, counts, weights, uniq, nullptr);
+    CK(cudaGetLastError());
+    return WMD_OK;
 }
 
 int wmd_pairs_padded_dev(wmd_handle E, const int32_t *a, int32_t L1, const int32_t *b, int32_t L2, int64_t npairs,
                          int32_t pad_id, int32_t mode, double *out, int32_t *status, void *stream)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (mode != WMD_MODE_PYEMD && mode != WMD_MODE_EXACT) return fail(WMD_EINVAL, "unknown mode %d", mode);
+    int base, rc;
+    if ((rc = parse_mode(E, mode, base))) return rc;
     if (npairs > 0 && (!a || !b)) return fail(WMD_EINVAL, "null ids");
     if (L1 <= 0 || L2 <= 0) return fail(WMD_EINVAL, "padded lengths must be positive");
     DocSide s1{}, s2{};
     s1.ids = a; s1.off = nullptr; s1.L = L1; s1.pad_id = pad_id; s1.has_pad = 1;
     s2.ids = b; s2.off = nullptr; s2.L = L2; s2.pad_id = pad_id; s2.has_pad = 1;
-    return run_dev_job(E, s1, s2, npairs * L1, npairs * L2, L1, L2, npairs, out, status, (cudaStream_t)stream, mode);
+    return run_dev_pairs(E, s1, s2, npairs * L1, npairs * L2, L1, L2, npairs, out, status, (cudaStream_t)stream, base);
 }
 
 int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t ndocs,
@@ -1177,6 +1432,7 @@ int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t 
     if (ndocs > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
     int rc;
     if ((rc = set_device(E))) return rc;
+    E->ids_are_rows = false;
     int32_t ml;
     if ((rc = scan_offsets(off, ndocs, ml, "documents"))) return rc;
     const int64_t base = off[0], total = off[ndocs] - base;
@@ -1221,7 +1477,15 @@ int wmd_allpairs_topk_host(wmd_handle E, const int32_t *idsA, const int64_t *off
                            int32_t *out_idx, double *out_dist, int64_t *stats, double *ms)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    return run_allpairs(E, idsA, offA, nA, idsB, offB, nB, k, row_begin, row_end, out_idx, out_dist, stats, ms);
+    return run_allpairs(E, idsA, offA, nA, idsB, offB, nB, k, row_begin, row_end, out_idx, out_dist, false, stats, ms);
+}
+
+int wmd_allpairs_topk_dev(wmd_handle E, const int32_t *idsA, const int64_t *offA, int64_t nA,
+                          const int32_t *idsB, const int64_t *offB, int64_t nB, int32_t k, int64_t row_begin, int64_t row_end,
+                          int32_t *out_idx_dev, double *out_dist_dev, int64_t *stats, double *ms)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    return run_allpairs(E, idsA, offA, nA, idsB, offB, nB, k, row_begin, row_end, out_idx_dev, out_dist_dev, true, stats, ms);
 }
 
 int wmd_emd_batch_host(wmd_handle E, const double *P, const double *Q, const double *D, int64_t nprob, int32_t n,

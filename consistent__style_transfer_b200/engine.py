@@ -7,6 +7,7 @@ synchronisation.  Nothing here computes: every number comes out of libwmd_b200.s
 from __future__ import annotations
 
 import ctypes
+from itertools import chain
 from typing import Optional, Sequence
 
 import numpy as np
@@ -17,6 +18,7 @@ from ._lib import c_f32p, c_f64p, c_i32p, c_i64p
 KERNEL_KINDS = ("nbow", "cost", "solve", "rwmd", "misc", "fused")
 MODE_PYEMD = 0      # the reference's value: pyemd's 1e6-grid integer optimum (bit-faithful)
 MODE_EXACT = 1      # additive: the real-valued transportation optimum in FP64
+IDS_ARE_ROWS = 0x100  # flag: this call's ids are table rows although a token map is installed
 _MODES = {"pyemd": MODE_PYEMD, "exact": MODE_EXACT, MODE_PYEMD: MODE_PYEMD, MODE_EXACT: MODE_EXACT}
 
 
@@ -30,10 +32,10 @@ def _ptr(a: Optional[np.ndarray], ct):
 
 def docs_to_csr(docs: Sequence[Sequence[int]]):
     """list of id lists -> (ids int32, off int64)"""
-    lens = np.fromiter((len(d) for d in docs), dtype=np.int64, count=len(docs))
     off = np.zeros(len(docs) + 1, np.int64)
-    np.cumsum(lens, out=off[1:])
-    ids = np.fromiter((t for d in docs for t in d), dtype=np.int32, count=int(off[-1]))
+    if len(docs):
+        np.cumsum(np.fromiter(map(len, docs), dtype=np.int64, count=len(docs)), out=off[1:])
+    ids = np.fromiter(chain.from_iterable(docs), dtype=np.int32, count=int(off[-1]))
     return ids, off
 
 
@@ -102,9 +104,10 @@ class WMDEngine:
 
     # -- scoring: host buffers --------------------------------------------------------------
     def wmd_pairs(self, ids1, off1, ids2, off2, out: Optional[np.ndarray] = None,
-                  status: Optional[np.ndarray] = None, mode="pyemd"):
+                  status: Optional[np.ndarray] = None, mode="pyemd", ids_are_rows: bool = False):
         """WMD of CSR-packed pairs held in host memory. Returns (float64[B], int32 status[B]).
-        mode "pyemd" (default) is the reference's value; "exact" the un-quantised FP64 optimum."""
+        mode "pyemd" (default) is the reference's value; "exact" the un-quantised FP64 optimum.
+        ids_are_rows: the ids are embedding rows even though a token map is installed."""
         ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
         off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
         B = off1.shape[0] - 1
@@ -115,9 +118,37 @@ class WMDEngine:
         if status is None:
             status = np.empty(B, np.int32)
         _lib.check(self._L.wmd_pairs_host(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p),
-                                          _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B, _MODES[mode],
+                                          _ptr(ids2, c_i32p), _ptr(off2, c_i64p), B,
+                                          _MODES[mode] | (IDS_ARE_ROWS if ids_are_rows else 0),
                                           _ptr(out, c_f64p), _ptr(status, c_i32p)))
         return out, status
+
+    def submit_pairs(self, ids1, off1, ids2, off2, mode="pyemd", ids_are_rows: bool = False) -> int:
+        """Asynchronous ``wmd_pairs``: stages the documents, queues copies and kernels and returns at once;
+        ``wait_pairs`` collects the result.  One job per engine may be in flight.  Returns the pair count."""
+        ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
+        off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
+        B = off1.shape[0] - 1
+        if off2.shape[0] - 1 != B:
+            raise ValueError("both sides must hold the same number of documents")
+        _lib.check(self._L.wmd_pairs_submit(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p), _ptr(ids2, c_i32p),
+                                            _ptr(off2, c_i64p), B, _MODES[mode] | (IDS_ARE_ROWS if ids_are_rows else 0)))
+        return B
+
+    def wait_pairs(self, npairs: int, out: Optional[np.ndarray] = None, status: Optional[np.ndarray] = None):
+        if out is None:
+            out = np.empty(npairs, np.float64)
+        if status is None:
+            status = np.empty(npairs, np.int32)
+        _lib.check(self._L.wmd_pairs_wait(self._handle(), _ptr(out, c_f64p), _ptr(status, c_i32p)))
+        return out, status
+
+    def workspace_bytes(self, npairs: int, max_len1: int, max_len2: int):
+        """(upper estimate of the device bytes a pair call of that size needs, bytes the handle holds now)"""
+        est = ctypes.c_int64(); res = ctypes.c_int64()
+        _lib.check(self._L.wmd_workspace_bytes(self._handle(), int(npairs), int(max_len1), int(max_len2),
+                                               ctypes.byref(est), ctypes.byref(res)))
+        return int(est.value), int(res.value)
 
     def wmd_pairs_ptr(self, ids1_ptr: int, off1_ptr: int, ids2_ptr: int, off2_ptr: int, npairs: int,
                       out_ptr: int, status_ptr: int = 0):
@@ -189,6 +220,36 @@ class WMDEngine:
                 "ms_bounds_select": ms[2], "ms_exact": ms[3]}
         return idx, dist, info
 
+    def allpairs_topk_cuda(self, idsA, offA, idsB, offB, k: int, row_begin: int = 0, row_end: Optional[int] = None,
+                           out_idx=None, out_dist=None):
+        """``allpairs_topk`` with the result left in torch CUDA tensors (int32 [rows, k], float64 [rows, k]; passed in or
+        allocated): what a multi-GPU job all-gathers over NCCL.  Returns info (and the tensors when it allocated them)."""
+        import torch
+        idsA, idsB = _np(idsA, np.int32), _np(idsB, np.int32)
+        offA, offB = _np(offA, np.int64), _np(offB, np.int64)
+        nA, nB = offA.shape[0] - 1, offB.shape[0] - 1
+        row_end = nA if row_end is None else int(row_end)
+        rows = max(row_end - int(row_begin), 0)
+        dev = torch.device("cuda", self.device)
+        made = out_idx is None or out_dist is None
+        if out_idx is None:
+            out_idx = torch.empty((rows, int(k)), dtype=torch.int32, device=dev)
+        if out_dist is None:
+            out_dist = torch.empty((rows, int(k)), dtype=torch.float64, device=dev)
+        if not (out_idx.is_cuda and out_dist.is_cuda and out_idx.is_contiguous() and out_dist.is_contiguous() and
+                out_idx.dtype == torch.int32 and out_dist.dtype == torch.float64 and
+                out_idx.numel() == rows * int(k) and out_dist.numel() == rows * int(k)):
+            raise ValueError("out_idx / out_dist must be contiguous CUDA tensors of [rows, k] int32 / float64")
+        stats = (ctypes.c_int64 * 8)()
+        ms = (ctypes.c_double * 4)()
+        _lib.check(self._L.wmd_allpairs_topk_dev(self._handle(), _ptr(idsA, c_i32p), _ptr(offA, c_i64p), nA,
+                                                 _ptr(idsB, c_i32p), _ptr(offB, c_i64p), nB, int(k), int(row_begin), row_end,
+                                                 out_idx.data_ptr(), out_dist.data_ptr(), stats, ms))
+        info = {"bounds": int(stats[0]), "exact_round1": int(stats[1]), "exact_round2": int(stats[2]),
+                "query_blocks": int(stats[3]), "ms_dist_table": ms[0], "ms_corpus_index": ms[1],
+                "ms_bounds_select": ms[2], "ms_exact": ms[3]}
+        return (out_idx, out_dist, info) if made else info
+
     # -- scoring: device tensors (torch) ----------------------------------------------------
     def wmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, out=None, status=None, mode="pyemd"):
         """CSR pairs in torch CUDA tensors (int32 ids, int64 offsets) -> float64 CUDA tensor.
@@ -208,9 +269,48 @@ class WMDEngine:
                                          B, _MODES[mode], out.data_ptr(), status.data_ptr(), stream))
         return out, status
 
+    def nbow_cuda(self, ids, off, max_len: int, want_weights: bool = True):
+        """``nbow`` on torch CUDA tensors (int32 ids, int64 offsets); outputs stay on the device, stream-ordered."""
+        import torch
+        if not (ids.is_cuda and off.is_cuda and ids.dtype == torch.int32 and off.dtype == torch.int64 and
+                ids.is_contiguous() and off.is_contiguous() and ids.device.index == self.device):
+            raise ValueError("expected contiguous CUDA tensors (int32 ids, int64 offsets) on the engine's device")
+        n = off.numel() - 1
+        dev = ids.device
+        rows = torch.full((ids.numel(),), -1, dtype=torch.int32, device=dev)
+        counts = torch.zeros(ids.numel(), dtype=torch.int32, device=dev)
+        weights = torch.zeros(ids.numel(), dtype=torch.float64, device=dev) if want_weights else None
+        uniq = torch.zeros(n, dtype=torch.int32, device=dev)
+        _lib.check(self._L.wmd_nbow_dev(self._handle(), ids.data_ptr(), off.data_ptr(), n, int(max_len), rows.data_ptr(),
+                                        counts.data_ptr(), weights.data_ptr() if want_weights else None, uniq.data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+        return rows, counts, weights, uniq
+
+    def rwmd_pairs_cuda(self, ids1, off1, ids2, off2, max_len1: int, max_len2: int, want_argmin: bool = True):
+        """``rwmd_pairs`` on torch CUDA tensors; every output stays on the device, stream-ordered, no host sync."""
+        import torch
+        for t, dt in ((ids1, torch.int32), (ids2, torch.int32), (off1, torch.int64), (off2, torch.int64)):
+            if not (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.device.index == self.device):
+                raise ValueError("expected contiguous CUDA tensors (int32 ids, int64 offsets) on the engine's device")
+        B = off1.numel() - 1
+        dev = ids1.device
+        f = lambda: torch.empty(B, dtype=torch.float64, device=dev)
+        lb, l1, l2 = f(), f(), f()
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        am1 = torch.full((ids1.numel(),), -1, dtype=torch.int32, device=dev) if want_argmin else None
+        am2 = torch.full((ids2.numel(),), -1, dtype=torch.int32, device=dev) if want_argmin else None
+        _lib.check(self._L.wmd_rwmd_pairs_dev(self._handle(), ids1.data_ptr(), off1.data_ptr(), ids1.numel(), int(max_len1),
+                                              ids2.data_ptr(), off2.data_ptr(), ids2.numel(), int(max_len2), B,
+                                              lb.data_ptr(), l1.data_ptr(), l2.data_ptr(),
+                                              am1.data_ptr() if want_argmin else None, am2.data_ptr() if want_argmin else None,
+                                              st.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        return dict(lb=lb, l1=l1, l2=l2, argmin_rows=am1, argmin_cols=am2, status=st)
+
     def wmd_pairs_padded(self, a, b, pad_id: int = 0, out=None, status=None):
         """Padded [B, L] torch CUDA id tensors (int32 or int64; pad_id skipped) -> float64[B] on device."""
         import torch
+        if not (a.is_cuda and b.is_cuda and a.device.index == self.device and b.device.index == self.device):
+            raise ValueError("expected CUDA tensors on the engine's device")
         if a.dtype != torch.int32:
             a = a.to(torch.int32)
         if b.dtype != torch.int32:
@@ -228,20 +328,23 @@ class WMDEngine:
                                                 B, int(pad_id), MODE_PYEMD, out.data_ptr(), status.data_ptr(), stream))
         return out, status
 
-    def wmd_pairs_torch(self, ids1, off1, ids2, off2):
-        """Host CSR (numpy) in, torch CUDA tensors (float64 scores, int32 status) out: the shape
-        ``sharding.wmd_pairs_sharded`` wants as its ``score_fn`` (scores stay on the device for the
-        NCCL gather)."""
+    def wmd_pairs_torch(self, ids1, off1, ids2, off2, out=None, status=None):
+        """Host CSR (numpy, pinned or pageable; offsets may start anywhere inside ``ids``) in, torch CUDA tensors
+        (float64 scores, int32 status) out: the shape ``sharding.wmd_pairs_sharded`` wants as its ``score_fn`` --
+        the library overlaps its chunked copies with the kernels and the scores stay on the device for the NCCL gather."""
         import torch
         dev = torch.device("cuda", self.device)
         ids1, ids2 = _np(ids1, np.int32), _np(ids2, np.int32)
         off1, off2 = _np(off1, np.int64), _np(off2, np.int64)
         B = off1.shape[0] - 1
-        if B == 0:
-            return torch.empty(0, dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
-        ml1, ml2 = int(np.diff(off1).max()), int(np.diff(off2).max())
-        t = lambda a: torch.from_numpy(a).to(dev, non_blocking=True)
-        return self.wmd_pairs_cuda(t(ids1), t(off1), t(ids2), t(off2), ml1, ml2)
+        if out is None:
+            out = torch.empty(B, dtype=torch.float64, device=dev)
+        if status is None:
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+        if B:
+            _lib.check(self._L.wmd_pairs_host_in_dev_out(self._handle(), _ptr(ids1, c_i32p), _ptr(off1, c_i64p), _ptr(ids2, c_i32p),
+                                                         _ptr(off2, c_i64p), B, MODE_PYEMD, out.data_ptr(), status.data_ptr()))
+        return out, status
 
     # -- instrumentation --------------------------------------------------------------------
     def set_profiling(self, enabled: bool):

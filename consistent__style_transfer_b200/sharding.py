@@ -38,6 +38,31 @@ def partition(cost: np.ndarray, world: int) -> np.ndarray:
     return np.maximum.accumulate(np.minimum(bounds, n))
 
 
+def partition_by_tokens(off1: np.ndarray, off2: np.ndarray, world: int, per_pair: int = 16) -> np.ndarray:
+    """``partition`` for the cost model "tokens of both sides + a per-pair constant" without touching the whole
+    batch: the CSR offsets ARE the running token counts, so every bound is one binary search over
+    f(p) = off1[p] + off2[p] + per_pair * p -- O(world * log B) instead of O(B) per call and rank."""
+    n = int(off1.shape[0]) - 1
+    bounds = np.zeros(world + 1, np.int64)
+    bounds[world] = n
+    if n == 0 or world == 1:
+        return bounds
+    base = int(off1[0]) + int(off2[0])
+    f = lambda p: int(off1[p]) + int(off2[p]) - base + per_pair * p
+    total = f(n)
+    for r in range(1, world):
+        want = total * r / world
+        lo, hi = 0, n
+        while lo < hi:                                   # smallest p with f(p) >= want
+            mid = (lo + hi) // 2
+            if f(mid) >= want:
+                hi = mid
+            else:
+                lo = mid + 1
+        bounds[r] = lo
+    return np.maximum.accumulate(bounds)
+
+
 def row_blocks(nrows: int, world: int) -> np.ndarray:
     """All-pairs mode: rank r owns rows [r*N/world, (r+1)*N/world) x all columns."""
     return (np.arange(world + 1, dtype=np.int64) * nrows) // world
@@ -87,22 +112,22 @@ def gather_scores(local_out, local_status, bounds: np.ndarray, group=None):
 
 
 def wmd_pairs_sharded(score_fn: Callable, ids1, off1, ids2, off2, group=None, gather: bool = True,
-                      rank: Optional[int] = None, world: Optional[int] = None):
-    """Every rank passes the SAME full CSR batch (host numpy); rank r scores its cost-balanced
-    contiguous slice with ``score_fn(ids1, off1, ids2, off2) -> (float64 tensor, int32 tensor)``
-    (e.g. ``lambda *a: engine.wmd_pairs_torch(*a)``) and, with ``gather``, every rank receives all
-    scores in input order.  Returns (out, status, (lo, hi))."""
+                      rank: Optional[int] = None, world: Optional[int] = None, balance: str = "tokens"):
+    """Every rank passes the SAME full CSR batch (host numpy); rank r scores its contiguous slice with
+    ``score_fn(ids1, off1_slice, ids2, off2_slice) -> (float64 tensor, int32 tensor)`` (e.g.
+    ``engine.wmd_pairs_torch``; the offset slices are views that keep pointing into the full id arrays, nothing is
+    copied) and, with ``gather``, every rank receives all scores in input order.  ``balance``: "tokens" (slices of
+    equal token count, found by binary search on the offsets) or "cost" (the quadratic per-pair model of
+    ``pair_cost``, one pass over the batch).  Returns (out, status, (lo, hi))."""
     dist = _dist()
     if world is None:
         world = dist.get_world_size(group) if dist else 1
     if rank is None:
         rank = dist.get_rank(group) if dist else 0
     off1 = np.asarray(off1, np.int64); off2 = np.asarray(off2, np.int64)
-    bounds = partition(pair_cost(off1, off2), world)
+    bounds = partition_by_tokens(off1, off2, world) if balance == "tokens" else partition(pair_cost(off1, off2), world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    a1, o1 = csr_slice(ids1, off1, lo, hi)
-    a2, o2 = csr_slice(ids2, off2, lo, hi)
-    out, st = score_fn(a1, o1, a2, o2)
+    out, st = score_fn(ids1, off1[lo:hi + 1], ids2, off2[lo:hi + 1])
     if gather:
         out, st = gather_scores(out, st, bounds, group=group)
     return out, st, (lo, hi)

@@ -12,7 +12,10 @@ What differs from the reference, and why:
   loop of per-pair gensim calls (src/wmd.py:36-44); results and fall-backs are identical
   (raw empty list -> ``max(len)``; ``inf`` -> ``(len1 + len2) / 2``).
 * ``tokenizer.ids_to_tokens`` (one Rust FFI call per id, src/vocab.py:26-27) is replaced by a
-  cached ``tokenizer id -> embedding row`` table built once per tokenizer.
+  ``tokenizer id -> embedding row`` table built once per tokenizer and installed on the DEVICE
+  (``wmd_set_token_map``): ``cal_wmd_label`` hands the raw tokenizer ids to the library.
+* ``cal_wmd_label_async`` (new) returns a handle at once and lets the label of batch k+1 be computed
+  while training step k runs (``wmd_pairs_submit`` / ``wmd_pairs_wait``).
 * training the embedding (gensim ``Word2Vec(sentences, iter=10)``, src/wmd.py:19) is out of scope:
   the non-lazy constructor delegates to gensim when it is importable and raises otherwise;
   ``from_embeddings`` / ``load`` take an existing ``[V, d]`` matrix.
@@ -42,7 +45,8 @@ def string_rank(index2word: Sequence[str]) -> np.ndarray:
 
 class KeyedVectors:
     """Stands where gensim's ``model.wv`` stands: ``wmdistance``, ``vectors``, ``index2word``,
-    ``vocab``, ``init_sims``.  Owns one ``WMDEngine`` (device copy of the table)."""
+    ``vocab``, ``init_sims``.  Owns ONE ``WMDEngine`` (device copy of the table, the word-distance
+    table, and the id -> row map of the tokenizer in use)."""
 
     def __init__(self, index2word: Sequence[str], vectors: np.ndarray, normalize: bool = False, device: int = 0):
         self.index2word: List[str] = list(index2word)
@@ -54,10 +58,12 @@ class KeyedVectors:
             raise ValueError("index2word holds duplicate tokens")
         self.device = int(device)
         self._rank = string_rank(self.index2word)
+        self._distance_table: Optional[bool] = None       # None: the library's policy
         self._engine = WMDEngine(vectors, normalize=normalize, device=self.device, rank=self._rank)
         self._vectors: Optional[np.ndarray] = None if normalize else vectors
-        self._dev_engines: Dict[int, WMDEngine] = {}      # id(token map) -> engine with that map installed
-        self._maps: Dict[int, np.ndarray] = {}
+        # id(tokenizer) -> (tokenizer, map): the strong reference keeps the id from being reused by another object
+        self._maps: Dict[int, tuple] = {}
+        self._installed: Optional[int] = None             # key of the map the engine holds right now
 
     # -- gensim-shaped attributes -----------------------------------------------------------
     @property
@@ -83,11 +89,10 @@ class KeyedVectors:
         if replace:
             v = self.vectors
             self._engine.close()
-            self._engine = WMDEngine(v, normalize=True, device=self.device, rank=self._rank)
+            self._engine = WMDEngine(v, normalize=True, device=self.device, rank=self._rank,
+                                     distance_table=self._distance_table)
             self._vectors = None
-            for e in self._dev_engines.values():
-                e.close()
-            self._dev_engines.clear()
+            self._installed = None
 
     # -- scoring ----------------------------------------------------------------------------
     def rows_of(self, document: Iterable[str]) -> List[int]:
@@ -105,19 +110,19 @@ class KeyedVectors:
             return []
         ids1, off1 = docs_to_csr([self.rows_of(d) for d in documents1])
         ids2, off2 = docs_to_csr([self.rows_of(d) for d in documents2])
-        out, _ = self._engine.wmd_pairs(ids1, off1, ids2, off2)
+        out, _ = self._engine.wmd_pairs(ids1, off1, ids2, off2, ids_are_rows=True)
         return out.tolist()
 
     def wmd_rows(self, ids1, off1, ids2, off2):
         """CSR lists of embedding rows (-1 = OOV) -> (float64[B], int32 status[B]) numpy."""
-        return self._engine.wmd_pairs(ids1, off1, ids2, off2)
+        return self._engine.wmd_pairs(ids1, off1, ids2, off2, ids_are_rows=True)
 
     # -- tokenizer ids ----------------------------------------------------------------------
     def token_map(self, tokenizer) -> np.ndarray:
         """tokenizer id -> embedding row (-1 when ``id_to_token`` gives None or an OOV token)."""
         key = id(tokenizer)
-        m = self._maps.get(key)
-        if m is None:
+        hit = self._maps.get(key)
+        if hit is None:
             inner = getattr(tokenizer, "tokenizer", tokenizer)      # BPETokenizer wraps a HF tokenizer
             n = len(tokenizer) if hasattr(tokenizer, "__len__") else inner.get_vocab_size()
             to_tok = inner.id_to_token if hasattr(inner, "id_to_token") else (lambda i: tokenizer.ids_to_tokens([i])[0])
@@ -126,37 +131,29 @@ class KeyedVectors:
                 t = to_tok(i)
                 if t is not None:
                     m[i] = self.vocab.get(t, -1)
-            self._maps[key] = m
-        return m
+            hit = self._maps[key] = (tokenizer, m)
+        return hit[1]
 
     def device_engine(self, tokenizer) -> WMDEngine:
-        """Engine with the tokenizer's id -> row table installed on the device (for the padded
-        CUDA-tensor entry: no host round trip, see ``WMDdistance.cal_wmd_padded``)."""
+        """The engine with the tokenizer's id -> row table installed on the device: tokenizer ids go to the
+        library as they are (``cal_wmd_label``, ``cal_wmd_padded``).  Switching between tokenizers re-installs
+        the (small) table; calls that pass embedding rows set ``ids_are_rows`` and are not affected."""
         key = id(tokenizer)
-        e = self._dev_engines.get(key)
-        if e is None:
-            e = WMDEngine(self.vectors, normalize=False, device=self.device, rank=self._rank,
-                          token_map=self.token_map(tokenizer))
-            if getattr(self, "_distance_table", False):
-                e.set_distance_table(True)
-            self._dev_engines[key] = e
-        return e
+        if self._installed != key:
+            self._engine.set_token_map(self.token_map(tokenizer))
+            self._installed = key
+        return self._engine
 
     def enable_distance_table(self, enabled: bool = True):
-        """New, additive: precompute the V x V word-distance table once (V * V * 4 bytes on the device) and let every
-        later ``wmdistance`` / ``cal_wmd_label`` / ``calculate_wmd_scores`` call look its cost tiles up instead of
-        recomputing them -- worth it for a scorer that lives as long as a training or evaluation run.  Values are
-        bit-identical (``include/wmd_b200.h``: ``wmd_set_distance_table``)."""
+        """The V x V word-distance table (V * V * 4 bytes on the device) is the library's default whenever it
+        fits its budget: every ``wmdistance`` / ``cal_wmd_label`` / ``calculate_wmd_scores`` call looks its costs
+        up instead of recomputing them, with bit-identical values (``include/wmd_b200.h``:
+        ``wmd_set_distance_table``).  ``True`` forces it on and builds it now, ``False`` forces the direct path."""
         self._distance_table = bool(enabled)
         self._engine.set_distance_table(enabled)
-        for e in self._dev_engines.values():
-            e.set_distance_table(enabled)
 
     def close(self):
         self._engine.close()
-        for e in self._dev_engines.values():
-            e.close()
-        self._dev_engines.clear()
 
 
 class _Model:
@@ -201,7 +198,7 @@ def load_vectors(path: str):
             wv = m.wv
             words = list(getattr(wv, "index2word", None) or wv.index_to_key)
             return words, np.asarray(wv.vectors, np.float32)
-        except ImportError:
+        except Exception:                                      # no gensim, or a gensim that cannot read this pickle
             from . import gensim_pickle
             return gensim_pickle.read(path)
     from . import gensim_pickle
@@ -268,23 +265,26 @@ class WMDdistance:
         return self.model.wv.wmdistance(x1, x2)
 
     def cal_wmd_label(self, xs1, xs2, tokenizer):             # src/wmd.py:34-45, one batched call
+        return self.cal_wmd_label_async(xs1, xs2, tokenizer, _sync=True).result()
+
+    def cal_wmd_label_async(self, xs1, xs2, tokenizer, _sync: bool = False) -> "PendingLabels":
+        """New, additive: starts the batch's labels on the GPU and returns at once; ``.result()`` gives the list
+        ``cal_wmd_label`` returns, ``.tensor(dtype)`` the tensor src/loader.py:68 builds from it.  The caller can
+        pad and convert the batch (or run the previous training step) while the kernels run.  One job per
+        ``WMDdistance`` may be in flight."""
         xs1, xs2 = list(xs1), list(xs2)
         n = min(len(xs1), len(xs2))                           # zip() semantics
         if n == 0:
-            return []
-        wv = self.model.wv
-        tmap = wv.token_map(tokenizer)
+            return PendingLabels(None, 0, None, None)
+        eng = self.model.wv.device_engine(tokenizer)          # tokenizer ids -> rows on the device
         ids1, off1 = docs_to_csr(xs1[:n])
         ids2, off2 = docs_to_csr(xs2[:n])
-        r1 = _map_ids(tmap, ids1)
-        r2 = _map_ids(tmap, ids2)
-        dist, _ = wv.wmd_rows(r1, off1, r2, off2)
-        len1 = np.diff(off1).astype(np.float64)
-        len2 = np.diff(off2).astype(np.float64)
-        empty = (len1 == 0) | (len2 == 0)
-        label = np.where(np.isinf(dist), (len1 + len2) / 2, dist)      # :41-42
-        label = np.where(empty, np.maximum(len1, len2), label)          # :37-38
-        return label.tolist()
+        pending = PendingLabels(eng, n, np.diff(off1), np.diff(off2))
+        if _sync:
+            pending._dist, _ = eng.wmd_pairs(ids1, off1, ids2, off2)
+        else:
+            eng.submit_pairs(ids1, off1, ids2, off2)
+        return pending
 
     def cal_wmd_padded(self, a, b, tokenizer, pad_id: int = 0):
         """New, additive: WMD of two padded ``[B, L]`` CUDA id tensors
@@ -303,9 +303,31 @@ class WMDdistance:
         return cls.from_embeddings(words, vectors, normalize=True, device=device)
 
 
-def _map_ids(tmap: np.ndarray, ids: np.ndarray) -> np.ndarray:
-    ids = np.asarray(ids, np.int64)
-    ok = (ids >= 0) & (ids < tmap.shape[0])
-    rows = np.full(ids.shape[0], -1, np.int32)
-    rows[ok] = tmap[ids[ok]]
-    return rows
+class PendingLabels:
+    """Handle of one ``cal_wmd_label_async`` batch.  ``result()`` applies the two fall-backs of src/wmd.py:37-44
+    (raw empty list -> ``max(len)``; ``inf`` -> ``(len1 + len2) / 2`` on the raw lengths)."""
+
+    def __init__(self, engine, n, len1, len2):
+        self._engine, self._n, self._len1, self._len2 = engine, n, len1, len2
+        self._dist = None
+        self._label = None
+
+    def _labels(self) -> np.ndarray:
+        if self._label is None:
+            if self._n == 0:
+                self._label = np.zeros(0, np.float64)
+                return self._label
+            if self._dist is None:
+                self._dist, _ = self._engine.wait_pairs(self._n)
+            len1, len2 = self._len1.astype(np.float64), self._len2.astype(np.float64)
+            label = np.where(np.isinf(self._dist), (len1 + len2) / 2, self._dist)       # :41-42
+            self._label = np.where((len1 == 0) | (len2 == 0), np.maximum(len1, len2), label)   # :37-38
+        return self._label
+
+    def result(self) -> List[float]:
+        return self._labels().tolist()
+
+    def tensor(self, dtype=None):
+        import torch
+        t = torch.from_numpy(self._labels())
+        return t.to(dtype) if dtype is not None else t

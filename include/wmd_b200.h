@@ -66,6 +66,9 @@ typedef struct wmd_engine *wmd_handle;
 #define WMD_MODE_PYEMD 0   /* pyemd emd_hat_gd_metric: 1e6-grid integer optimum (bit-faithful to the reference) */
 #define WMD_MODE_EXACT 1   /* additive: the real-valued transportation optimum in FP64 (no grid, no cancellation);
                               differs from the reference's value by ~1e-6 relative */
+/* flag, OR-ed into `mode`: the ids of THIS call are embedding-table rows even though a token map is installed
+ * (gensim's wv.wmdistance(tokens) and cal_wmd_label(tokenizer ids) served by one handle, src/wmd.py:31-45) */
+#define WMD_IDS_ARE_ROWS 0x100
 
 /* lifetime ------------------------------------------------------------------------------------ */
 
@@ -93,6 +96,23 @@ int wmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
                    const int32_t *ids2, const int64_t *off2, int64_t npairs,
                    int32_t mode, double *out, int32_t *status);
 
+/* wmd_pairs_host whose results stay on the device: documents in HOST memory (chunked copies overlapped with the
+ * kernels, as wmd_pairs_host), out_dev[npairs] / status_dev[npairs] (may be NULL) DEVICE arrays, complete on return.
+ * The multi-GPU layer scores a rank's slice this way and hands the device array to the NCCL gather. */
+int wmd_pairs_host_in_dev_out(wmd_handle h, const int32_t *ids1, const int64_t *off1,
+                              const int32_t *ids2, const int64_t *off2, int64_t npairs,
+                              int32_t mode, double *out_dev, int32_t *status_dev);
+
+/* Asynchronous host entry for batches of the in-loop caller's size (src/loader.py:60 -> src/wmd.py:34-45): the
+ * label of batch k+1 is computed while training step k runs.  wmd_pairs_submit copies the documents (pageable or
+ * pinned HOST memory; the caller's buffers are free again on return) into pinned staging the handle owns, queues
+ * copies and kernels on the handle's streams and returns; wmd_pairs_wait blocks until the job is done and copies
+ * out[npairs] / status[npairs] (may be NULL) to the caller.  One job per handle may be in flight; every other
+ * scoring entry fails with WMD_EINVAL until it has been waited for. */
+int wmd_pairs_submit(wmd_handle h, const int32_t *ids1, const int64_t *off1,
+                     const int32_t *ids2, const int64_t *off2, int64_t npairs, int32_t mode);
+int wmd_pairs_wait(wmd_handle h, double *out, int32_t *status);
+
 /* Same on device buffers, stream-ordered.  max_len1/max_len2 bound the document lengths of
  * each side (needed to size the launch without a host sync); total1/total2 are off1[npairs],
  * off2[npairs].  */
@@ -113,6 +133,11 @@ int wmd_pairs_padded_dev(wmd_handle h, const int32_t *a, int32_t L1, const int32
 int wmd_nbow_host(wmd_handle h, const int32_t *ids, const int64_t *off, int64_t ndocs,
                   int32_t *rows, int32_t *counts, double *weights, int32_t *uniq);
 
+/* wmd_nbow_host on device buffers: ids / off / outputs are DEVICE pointers, max_len bounds the
+ * document length, the launch is ordered on `stream`, no host sync.  weights may be NULL. */
+int wmd_nbow_dev(wmd_handle h, const int32_t *ids, const int64_t *off, int64_t ndocs, int32_t max_len,
+                 int32_t *rows, int32_t *counts, double *weights, int32_t *uniq, void *stream);
+
 /* Relaxed WMD lower bound per pair: lb = max(l1, l2), l1 = sum_i w1[i] min_j c[i][j] (FP64,
  * canonical order), with the argmin column of every doc1 row / argmin row of every doc2
  * column (lowest index on ties) written at the documents' CSR offsets.  l1/l2/argmins may be NULL. */
@@ -120,6 +145,13 @@ int wmd_rwmd_pairs_host(wmd_handle h, const int32_t *ids1, const int64_t *off1,
                         const int32_t *ids2, const int64_t *off2, int64_t npairs,
                         double *lb, double *l1, double *l2,
                         int32_t *argmin_rows, int32_t *argmin_cols, int32_t *status);
+
+/* wmd_rwmd_pairs_host on device buffers, stream-ordered, no host sync; arguments as wmd_pairs_dev.  The argmin
+ * arrays are indexed by the documents' CSR offsets (total1 / total2 entries). */
+int wmd_rwmd_pairs_dev(wmd_handle h, const int32_t *ids1, const int64_t *off1, int64_t total1, int32_t max_len1,
+                       const int32_t *ids2, const int64_t *off2, int64_t total2, int32_t max_len2, int64_t npairs,
+                       double *lb, double *l1, double *l2, int32_t *argmin_rows, int32_t *argmin_cols,
+                       int32_t *status, void *stream);
 
 /* pyemd.emd(first_histogram, second_histogram, distance_matrix, extra_mass_penalty) for nprob
  * independent problems of n <= 31 bins each: P, Q are [nprob, n] float64 HOST arrays, D is one
@@ -146,6 +178,14 @@ int wmd_allpairs_topk_host(wmd_handle h, const int32_t *idsA, const int64_t *off
                            int64_t row_begin, int64_t row_end, int32_t *out_idx, double *out_dist,
                            int64_t *stats, double *ms);
 
+/* wmd_allpairs_topk_host whose result stays on the device: the documents are HOST arrays as above
+ * (they are staged once), out_idx_dev / out_dist_dev are DEVICE arrays of [(row_end - row_begin), k] entries, complete
+ * on return -- a multi-GPU job hands them straight to the NCCL all-gather of the per-row results. */
+int wmd_allpairs_topk_dev(wmd_handle h, const int32_t *idsA, const int64_t *offA, int64_t nA,
+                          const int32_t *idsB, const int64_t *offB, int64_t nB, int32_t k,
+                          int64_t row_begin, int64_t row_end, int32_t *out_idx_dev, double *out_dist_dev,
+                          int64_t *stats, double *ms);
+
 /* Word-distance table of the pair entries (the reference has no counterpart: gensim's wmdistance,
  * models/keyedvectors.py [gensim 3.8], recomputes every word distance on every call).  A handle keeps the float32
  * distance of every two rows of its embedding table -- V * V * 4 bytes of device memory, computed ONCE by the pair
@@ -161,6 +201,12 @@ int wmd_set_distance_table(wmd_handle h, int32_t enabled);
 /* bytes the table takes (V * V * 4), wall milliseconds its one-off build took (0 until built), whether the pair
  * entries use it, whether it is resident.  Any pointer may be NULL. */
 int wmd_distance_table_info(wmd_handle h, int64_t *bytes, double *build_ms, int32_t *enabled, int32_t *resident);
+
+/* Device memory of a handle.  *estimate: upper bound of the bytes a pair call of npairs documents
+ * of at most max_len1 / max_len2 tokens needs in total (embedding table, maps, word-distance table under the current
+ * policy, both workspace slots); *resident: what the handle holds right now.  Either pointer may be NULL. */
+int wmd_workspace_bytes(wmd_handle h, int64_t npairs, int32_t max_len1, int32_t max_len2,
+                        int64_t *estimate, int64_t *resident);
 
 /* instrumentation ----------------------------------------------------------------------------- */
 

@@ -89,3 +89,24 @@ def test_allpairs_k_equals_corpus_and_book_shape(oracle):
     eng = WMDEngine(table)
     _check(table, (idsA, offA), (idsB, offB), 24, oracle, eng)      # k == |B|: a full sort of every row
     eng.close()
+
+
+def test_allpairs_unnormalised_table_long_documents_and_device_output(oracle):
+    """An un-normalised embedding table (row norms ~10: distances of 10-20, where an absolute pruning margin
+    sized for unit vectors would be too small) with documents of up to 120 tokens; and the device-output entry
+    (wmd_allpairs_topk_dev) returns the same bits as the host entry."""
+    import torch
+    from consistent__style_transfer_b200.engine import WMDEngine
+    V = 700
+    rng = np.random.default_rng(19)
+    table = (rng.standard_normal((V, 48)) * 1.5).astype(np.float32)
+    idsA, offA, idsB, offB = workload.make_pairs(260, "uniform:1-120", "independent", V=V, seed=29)
+    idsA, offA = idsA[:offA[40]], offA[:41]
+    eng = WMDEngine(table)
+    _check(table, (idsA, offA), (idsB, offB), 9, oracle, eng)
+    idx, dist, _ = eng.allpairs_topk(idsA, offA, idsB, offB, 9, 5, 33)
+    didx, ddist, info = eng.allpairs_topk_cuda(idsA, offA, idsB, offB, 9, 5, 33)
+    torch.cuda.synchronize()
+    assert didx.is_cuda and np.array_equal(didx.cpu().numpy(), idx) and ddist.cpu().numpy().tobytes() == dist.tobytes()
+    assert info["bounds"] == 28 * 260
+    eng.close()

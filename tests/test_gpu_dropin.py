@@ -137,6 +137,7 @@ def test_collate_pretrain_matches_reference_pipeline(oracle, cases):
 
     import torch
     from golden_util import noise_cases
+    from consistent__style_transfer_b200 import data_util
     from consistent__style_transfer_b200.loader import collate_pretrain
     from consistent__style_transfer_b200.wmd import WMDdistance
     c = cases[0]
@@ -154,7 +155,6 @@ def test_collate_pretrain_matches_reference_pipeline(oracle, cases):
         out = collate_pretrain(bpe, w)(samples)
         assert len(out) == 6 and [t.dtype for t in out] == [torch.long] * 5 + [torch.float32]
         # replay the same draws to recover the noised sentences the labels were computed on
-        from consistent__style_transfer_b200 import data_util
         np.random.seed(nc["seed"]); random.seed(nc["seed"] + 1000)
         n1 = data_util.transfer_noise([list(s) for s in batch], p=0.15)
         n2 = data_util.transfer_noise([list(s) for s in batch], p=0.15)
@@ -162,3 +162,49 @@ def test_collate_pretrain_matches_reference_pipeline(oracle, cases):
         assert out[5].numpy().tobytes() == np.asarray(want, np.float32).tobytes()
         assert out[0].shape[0] == len(batch) and out[1].shape[0] == len(batch)
         assert out[4].tolist() == [i % 2 for i in range(len(batch))]
+        # the four id matrices are the padded sentences themselves (loader.py:54-58)
+        assert out[0].tolist() == data_util.align(batch, 0)[0] and out[1].tolist() == data_util.align(n1, 0)[0]
+        assert out[2].tolist() == data_util.align(n2, 0)[0]
+    w.model.wv.close()
+
+
+def test_async_labels_prefetcher_and_device_collate(oracle, cases):
+    """cal_wmd_label_async == cal_wmd_label; LabelPrefetcher yields what collate_pretrain yields with the labels
+    of the next batch in flight; collate_pretrain_cuda's labels are the WMD of ITS noised tensors."""
+    import random
+
+    import torch
+    from golden_util import noise_cases
+    from consistent__style_transfer_b200.loader import LabelPrefetcher, collate_pretrain, collate_pretrain_cuda
+    from consistent__style_transfer_b200.wmd import WMDdistance
+    c = cases[0]
+    w = WMDdistance.from_embeddings(c["vocab"], c["raw_vectors"], normalize=True)
+    V = len(c["vocab"])
+    bpe = FakeBPE(["<pad>", "<s>", "</s>", "<unk>"] + list(c["vocab"]))
+    batches = []
+    for nc in noise_cases()[:3]:
+        batch = [[4 + (t % V) for t in s] for s in nc["batch"]]
+        batches.append([(s, i % 2) for i, s in enumerate(batch)])
+    xs1 = [s for s, _ in batches[0]]; xs2 = [s[::-1][:-1] for s, _ in batches[0]]
+    p = w.cal_wmd_label_async(xs1, xs2, bpe)
+    with pytest.raises(RuntimeError, match="in flight"):
+        w.model.wv.wmdistance(["a"], ["b"])                     # one job per handle
+    assert same_floats(p.result(), w.cal_wmd_label(xs1, xs2, bpe))
+    assert p.tensor(torch.float).dtype == torch.float32
+    assert w.cal_wmd_label_async([], [], bpe).result() == []
+    np.random.seed(3); random.seed(4)
+    seq = [collate_pretrain(bpe, w)(b) for b in batches]
+    np.random.seed(3); random.seed(4)
+    pre = list(LabelPrefetcher(batches, bpe, w))
+    assert len(pre) == len(seq)
+    for a, b in zip(seq, pre):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    out = collate_pretrain_cuda(bpe, w, generator=g)(batches[0])
+    assert all(t.is_cuda for t in out) and out[5].dtype == torch.float32 and out[1].shape[0] == len(batches[0])
+    n1 = [[t for t in row if t != 0] for row in out[1].tolist()]
+    n2 = [[t for t in row if t != 0] for row in out[2].tolist()]
+    want = w.cal_wmd_label(n1, n2, bpe)
+    assert out[5].cpu().numpy().tobytes() == np.asarray(want, np.float32).tobytes()
+    assert sorted(t for s in n1 for t in s) == sorted(t for s, _ in batches[0] for t in s)
+    w.model.wv.close()

@@ -310,3 +310,52 @@ def test_exact_mode_matches_lp(eng_mod, oracle, shape, B, d):
             assert abs(got[p] - want) <= 1e-9 * max(1.0, want), (p, got[p], want)
             assert abs(got[p] - ref[p]) <= 2e-5 * max(1.0, want)
     e.close()
+
+
+def test_async_and_device_forms_match_the_host_entries(eng_mod, oracle):
+    """SURVEY 8(b) ABI: wmd_pairs_submit / wmd_pairs_wait, wmd_nbow_dev, wmd_rwmd_pairs_dev, wmd_workspace_bytes."""
+    import torch
+    V = 1500
+    table = workload.make_table(V, 100, seed=4)
+    ids1, off1, ids2, off2 = workload.make_pairs(3000, "book", "independent", V=V, seed=31)
+    e = eng_mod.WMDEngine(table)
+    want, wst = e.wmd_pairs(ids1, off1, ids2, off2)
+    for _ in range(2):                                            # the second job reuses the pinned staging
+        n = e.submit_pairs(ids1, off1, ids2, off2)
+        with pytest.raises(RuntimeError, match="in flight"):
+            e.wmd_pairs(ids1, off1, ids2, off2)
+        got, st = e.wait_pairs(n)
+        assert got.tobytes() == want.tobytes() and np.array_equal(st, wst)
+    with pytest.raises(RuntimeError, match="no submitted job"):
+        e.wait_pairs(1)
+    # a token map on the device, rows passed through the flag
+    tmap = np.concatenate([[-1, -1], np.arange(V)]).astype(np.int32)
+    e.set_token_map(tmap)
+    g2, s2 = e.wmd_pairs(ids1 + 2, off1, ids2 + 2, off2)
+    g3, s3 = e.wmd_pairs(ids1, off1, ids2, off2, ids_are_rows=True)
+    assert g2.tobytes() == want.tobytes() and g3.tobytes() == want.tobytes() and np.array_equal(s2, wst) and np.array_equal(s3, wst)
+    e.set_token_map(None)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    ml1, ml2 = int(np.diff(off1).max()), int(np.diff(off2).max())
+    # nBOW on the device
+    rows, counts, weights, uniq = e.nbow(ids1, off1)
+    drows, dcounts, dweights, duniq = e.nbow_cuda(t(ids1), t(off1), ml1)
+    torch.cuda.synchronize()
+    assert np.array_equal(duniq.cpu().numpy(), uniq)
+    for p in range(0, 3000, 7):
+        a, u = off1[p], uniq[p]
+        assert np.array_equal(drows.cpu().numpy()[a:a + u], rows[a:a + u]) and np.array_equal(dcounts.cpu().numpy()[a:a + u], counts[a:a + u])
+        assert dweights.cpu().numpy()[a:a + u].tobytes() == weights[a:a + u].tobytes()
+    # RWMD on the device (70 000 pairs: several chunks on both streams, argmins at absolute offsets)
+    i1, o1, i2, o2 = workload.make_pairs(70000, "yelp", "independent", V=V, seed=33)
+    h = e.rwmd_pairs(i1, o1, i2, o2)
+    d = e.rwmd_pairs_cuda(t(i1), t(o1), t(i2), t(o2), 20, 20)
+    torch.cuda.synchronize()
+    for k in h:
+        assert np.asarray(h[k]).tobytes() == d[k].cpu().numpy().tobytes(), k
+    est, res = e.workspace_bytes(70000, 20, 20)
+    assert res > table.nbytes and est >= V * V * 4 and est > 0
+    est2, _ = e.workspace_bytes(70000, 256, 256)
+    assert est2 > est
+    e.close()

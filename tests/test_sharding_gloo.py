@@ -78,3 +78,17 @@ def test_csr_slice_rebases_offsets():
     ids, off = workload.to_csr([[1, 2], [], [3], [4, 5, 6]])
     a, o = sharding.csr_slice(ids, off, 1, 4)
     assert list(a) == [3, 4, 5, 6] and list(o) == [0, 0, 1, 4]
+
+
+def test_partition_by_tokens_matches_the_linear_cost_model():
+    ids1, off1, ids2, off2 = workload.make_pairs(20_000, "uniform:1-90", "independent", V=500, seed=3)
+    cost = (np.diff(off1) + np.diff(off2) + 16).astype(np.float64)
+    for world in (1, 2, 3, 8):
+        b = sharding.partition_by_tokens(off1, off2, world)
+        assert b[0] == 0 and b[-1] == 20_000 and np.all(np.diff(b) >= 0)
+        per = [cost[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert max(per) - min(per) <= 2 * cost.max() + 1
+        # a view that starts in the middle of the batch partitions its own pairs
+        v = sharding.partition_by_tokens(off1[5000:15001], off2[5000:15001], world)
+        assert v[-1] == 10_000 and np.all(np.diff(v) >= 0)
+    assert list(sharding.partition_by_tokens(np.zeros(1, np.int64), np.zeros(1, np.int64), 3)) == [0, 0, 0, 0]
