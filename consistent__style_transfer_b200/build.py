@@ -18,6 +18,29 @@ NVCC_FLAGS = [
 ]
 
 
+def csrpack_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "_csrpack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_csrpack(force: bool = False) -> str:
+    """The host-side list -> CSR packer (csrc/csrpack.c, CPython C API, no CUDA)."""
+    import sysconfig
+    out, src = csrpack_path(), os.path.join(CSRC, "csrpack.c")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for _csrpack")
+    tmp = out + f".{os.getpid()}.tmp"
+    res = subprocess.run([cc, "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], "-o", tmp, src],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building _csrpack failed: " + res.stderr[-400:])
+    os.replace(tmp, out)
+    return out
+
+
 def nvcc_path() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -37,14 +60,27 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libwmd_b200.so")
-    with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:                       # ranks of one job may all find the library stale
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():                          # another process built it while we waited
+            return LIB
+        tmp = LIB + f".{os.getpid()}.tmp"
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed building libwmd_b200.so")
+        os.replace(tmp, LIB)                                       # never a half-written file at the final path
+        with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
+            f.write(res.stdout + res.stderr)
+    try:
+        build_csrpack(force)
+    except Exception as exc:                                       # the packer is an accelerator, not a dependency
+        sys.stderr.write(f"[build] _csrpack not built: {exc}\n")
     return LIB
 
 

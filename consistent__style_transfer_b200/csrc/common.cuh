@@ -15,7 +15,8 @@ constexpr int kIntInf = 0x3fffffff;      // "infinite" tentative distance (sums 
 constexpr int kClsNone = 0;              // nothing to do (early-out already written)
 constexpr int kClsA = 1;                 // residual rows <= 32 and columns (incl. dummy) <= 32
 constexpr int kClsB = 2;                 // <= 64 / <= 64
-constexpr int kClsC = 3;                 // anything up to 256 x 257
+constexpr int kClsC = 3;                 // <= 128 / <= 160
+constexpr int kClsD = 4;                 // anything up to 256 x 257
 constexpr int kMetaSwap = 8;             // doc2 is the heavier (supplying) side
 
 // One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).

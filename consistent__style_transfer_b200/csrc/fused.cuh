@@ -72,8 +72,13 @@ __device__ __forceinline__ void fused_side(const DocSide &s, const Vocab &vc, in
     const bool first = valid && (__ffs(same) - 1 == lane);
     const unsigned fm = __ballot_sync(kFull, first);
     u = __popc(fm);
+    // canonical position = number of smaller unique keys: the unique keys go to shared memory unsorted (sc is free
+    // until the counts land in it) and every first occurrence counts against broadcast reads
+    if (first) sc[__popc(fm & ((1u << lane) - 1u))] = key;
+    __syncwarp();
     int pos = 0;
-    for (unsigned m = fm; m; m &= m - 1) pos += (__shfl_sync(kFull, key, __ffs(m) - 1) < key);
+    for (int j = 0; j < u; ++j) pos += (sc[j] < key);
+    __syncwarp();
     if (first) { sk[pos] = key; sr[pos] = row; sc[pos] = __popc(same); }
     __syncwarp();
     const bool mine = lane < u;
@@ -82,7 +87,8 @@ __device__ __forceinline__ void fused_side(const DocSide &s, const Vocab &vc, in
     cnt_o = mine ? sc[lane] : 0;
 }
 
-__global__ void __launch_bounds__(128, 8)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
 {
     extern __shared__ __align__(16) int smem_i[];
@@ -240,19 +246,29 @@ wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
             const int rowP = flip ? packedC : packedR, colP = flip ? packedR : packedC;
             const int supply = lane < nrow ? (rowP >> 8) : ((flip && lane == nrow) ? diff : 0);
             const int deficit = lane < ncol ? (colP >> 8) : ((!flip && lane == ncol) ? diff : 0);
-            const int cidx = colP & 0xff;
             const bool rows_doc1 = swap == flip;
-            for (int rI = 0; rI < mm; ++rI) {
-                const int ridx = __shfl_sync(kFull, rowP, rI) & 0xff;
-                int ic = 0;
-                if (lane < ncol && rI < nrow) {
-                    const float dv = rows_doc1 ? tileF[ridx * u2 + cidx] : tileF[cidx * u2 + ridx];
-                    ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+            // quantised costs of the residual sub-tile (S6(d)), 32 cells per step; the dummy row / column costs 0
+            {
+                const int ncell = mm * ncc;
+                const float inv = 1.0f / (float)ncc;
+                for (int c0 = 0; c0 < ncell; c0 += kWarp) {
+                    const int c = c0 + lane;
+                    const bool live = c < ncell;
+                    const int cc = live ? c : 0;
+                    const int rI = (int)(((float)cc + 0.5f) * inv);      // c / ncc (exact: c < 2^16)
+                    const int cI = cc - rI * ncc;
+                    const int ridx = __shfl_sync(kFull, rowP, rI) & 0xff, cidx = __shfl_sync(kFull, colP, cI) & 0xff;
+                    int ic = 0;
+                    if (live && rI < nrow && cI < ncol) {
+                        const float dv = rows_doc1 ? tileF[ridx * u2 + cidx] : tileF[cidx * u2 + ridx];
+                        ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                    }
+                    if (live) cost[rI * ldc + cI] = ic;
                 }
-                if (lane < ncc) cost[rI * ldc + lane] = ic;
             }
+            sridx[lane] = deficit;                               // the compaction list is dead: it keeps the deficits for the dual objective
             __syncwarp();
-            opt = transport_solve_small(mm, ncc, ldc, cost, flow, cmask, supply, deficit, lane);
+            opt = transport_solve_small(mm, ncc, ldc, cost, flow, cmask, supply, deficit, lane, sridx);
         }
         if (lane == 0) {
             const double maxc_d = (double)maxc_f;

@@ -108,8 +108,11 @@ __device__ __forceinline__ void atom_and_s32(unsigned a, unsigned v)
     asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+// deficit0 (optional, shared memory, [32]): the columns' deficits as they were handed in.  With it the optimum is read
+// off the duals -- at termination every arc that carries flow is tight, so sum f c = sum u_r supply_r + sum v_c deficit_c
+// exactly (integers) -- instead of a pass over the flow and cost matrices.
 __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ldc, const int *cost_p, int *flow_p, unsigned *cmask_p,
-                                                           int supply, int deficit, int lane)
+                                                           int supply, int deficit, int lane, const int *deficit0 = nullptr)
 {
     const unsigned cost = smem_addr(cost_p), flow = smem_addr(flow_p), cmask = smem_addr(cmask_p);
     const unsigned ld4 = (unsigned)ldc * 4u, lane4 = (unsigned)lane * 4u;
@@ -208,7 +211,8 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
         }
     }
     long long tot = 0;
-    if (iscol)
+    if (deficit0) tot = (long long)u * (long long)supply + (long long)v * (long long)deficit0[lane];
+    else if (iscol)
         for (int i = 0; i < m; ++i) tot += (long long)lds32(flow + i * ld4 + lane4) * (long long)lds32(cost + i * ld4 + lane4);
     return warp_sum_ll(tot);
 }
@@ -321,8 +325,9 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
                     }
                     if (lane < ncc) cost[rI * ldc + lane] = ic;
                 }
+                sridx[lane] = deficit;                           // the compaction list is dead: it keeps the deficits for the dual objective
                 __syncwarp();
-                opt = transport_solve_small(mm, ncc, ldc, cost, flow, cmask, supply, deficit, lane);
+                opt = transport_solve_small(mm, ncc, ldc, cost, flow, cmask, supply, deficit, lane, sridx);
             }
         }
         if (lane == 0) {
@@ -339,13 +344,14 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Classes B (<= 64 x 64) and C (<= 256 x 257): the class-A design with KR row words and KC column
+// Classes B (<= 64 x 64), C (<= 128 x 160) and D (<= 256 x 257): the class-A design with KR row words and KC column
 // words.  Lane L is rows L + 32k (k < KR) and columns L + 32k (k < KC); duals, tentative distances and
 // tree predecessors stay in registers, the tree / used-column sets are KR / KC warp-uniform words,
 // and cmask[j][KR] (shared memory) says which rows ship into column j.  The flow matrix is only ever
 // touched along augmenting paths and where cmask has a bit, so it lives in global scratch and is never
 // cleared (a cell is written, not added to, when its bit is off).  Costs: shared memory (class B) or
-// L2-resident global scratch (class C).  The previous version kept dense cost AND flow per warp in
+// L2-resident global scratch (classes C and D; every selection step walks all KC column words and every new tree row
+// all KR row words, so a 100 x 100 problem runs ~2x faster in the <4, 5> instance than in <8, 9>).  The previous version kept dense cost AND flow per warp in
 // shared memory (35 kB: 4 warps per SM) and found the rows of a saturated column by scanning a flow
 // column with dependent loads; profiles/README.md has the before / after.
 // ------------------------------------------------------------------------------------------------

@@ -88,8 +88,8 @@ struct ProfRec { int kind; cudaEvent_t a, b; };
 
 // unsigned slots of Workspace::counters
 constexpr size_t kCounterBytes = 128;
-constexpr int kCtrFused = 4;                    // fused kernel's work-claim counter
-constexpr int kCtrNBig = 5;                     // length of Workspace::biglist
+constexpr int kCtrFused = 6;                    // fused kernel's work-claim counter (slots 1..4: the solver classes)
+constexpr int kCtrNBig = 7;                     // length of Workspace::biglist
 constexpr int kCtrCost = 8;                     // general cost kernel's claim counter
 constexpr int kCtrStages = 9;                   // planned stages of the fast cost path
 constexpr int kCtrDmax = 12;                    // largest entry of the word-distance table (float bits)
@@ -126,6 +126,7 @@ struct wmd_engine {
     void *pin_in = nullptr, *pin_out = nullptr;  // wmd_pairs_submit / wmd_pairs_wait: handle-owned pinned staging
     size_t pin_in_cap = 0, pin_out_cap = 0;
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
+    int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
     cudaStream_t ap_stream = nullptr;
@@ -133,6 +134,7 @@ struct wmd_engine {
     unsigned long long *stats = nullptr;        // device [6]
     bool profiling = false;
     int solve_blocks_per_sm = 8;                 // K3 grid cap per SM (WMD_SOLVE_BLOCKS): fewer leaves room for a co-resident K2b
+    int solve_c_blocks = 4;                      // class C (<4, 5>) blocks of 4 warps per SM (WMD_SOLVE_C_BLOCKS)
     int fast_stage_cap = kFastMaxStages;         // K2b ring depth cap (WMD_FAST_S)
     int slot_mask = 1;                           // 0 (WMD_SERIAL=1): every chunk on one stream, for clean per-kernel timings
     std::vector<ProfRec> prof;
@@ -375,16 +377,18 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
                    const unsigned int *nlist, bool gather)
 {
     int rc;
-    for (int cls = kClsA; cls <= kClsC; ++cls) {
+    for (int cls = kClsA; cls <= kClsD; ++cls) {
         if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
         if (cls == kClsC && ML < 64) continue;
+        if (cls == kClsD && ML <= 128) continue;     // m > 128 or nc > 160
         SolveArgs S;
         S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
-        const int cap = cls == kClsA ? 32 : (cls == kClsB ? 64 : kMaxDocLen + 1);
-        S.mr = std::min(cap, ML); S.mc = std::min(cap, ML + 1);
+        const int capr = cls == kClsA ? 32 : cls == kClsB ? 64 : cls == kClsC ? 128 : kMaxDocLen;
+        const int capc = cls == kClsA ? 32 : cls == kClsB ? 64 : cls == kClsC ? 160 : kMaxDocLen + 1;
+        S.mr = std::min(capr, ML); S.mc = std::min(capc, ML + 1);
         if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
         S.ldc = S.mc | 1;
-        S.use_global = cls == kClsC;
+        S.use_global = cls >= kClsC;
         S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
         S.tiles = tiles; S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
         S.counter = W.counters.as<unsigned int>() + cls;
@@ -395,11 +399,13 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         int wpb = 8;
         size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
                         : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
+                        : cls == kClsC ? solve_multi_smem_per_warp<4, 5>(S.mr, S.mc, S.ldc, true)
                                        : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
         int blocks_per_sm = E->solve_blocks_per_sm;
         if (cls == kClsA) { wpb = 4; blocks_per_sm *= 2; }                                // __launch_bounds__(128, 9)
         if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
-        if (cls == kClsC) { wpb = 4; blocks_per_sm = 3; }                                 // 163 registers: 3 blocks of 4 warps per SM
+        if (cls == kClsC) { wpb = 4; blocks_per_sm = E->solve_c_blocks; }
+        if (cls == kClsD) { wpb = 4; blocks_per_sm = 3; }                                 // 168 registers: 3 blocks of 4 warps per SM
         while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
         const size_t smem = per_warp * wpb;
         const int ppw = multi ? 1 : 8;                                                    // pairs per warp below which the grid shrinks
@@ -420,6 +426,8 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         if (cls == kClsA) { if (gather) WMD_LAUNCH_SOLVER(emd_solve_small_kernel<true>); else WMD_LAUNCH_SOLVER(emd_solve_small_kernel<false>); }
         else if (cls == kClsB) {
             if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, false>));
+        } else if (cls == kClsC) {
+            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<4, 5, true, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<4, 5, true, false>));
         } else {
             if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, false>));
         }
@@ -462,16 +470,17 @@ int run_chunk_fused(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide 
     {
         const int wpb = 4;
         const size_t smem = fused_smem_per_warp(F.cap, F.ldc) * wpb;
+        auto kern = E->fused_minb >= 10 ? wmd_fused_small_kernel<10> : E->fused_minb == 9 ? wmd_fused_small_kernel<9> : wmd_fused_small_kernel<8>;
         if (smem != E->fused_smem_cached) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(wmd_fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wmd_fused_small_kernel, wpb * 32, smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, wpb * 32, smem));
             if (nb < 1) return fail(WMD_ECUDA, "wmd_fused_small_kernel cannot be resident");
             E->fused_blocks_per_sm = nb; E->fused_smem_cached = smem;
         }
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * E->fused_blocks_per_sm));
         Prof pr(E, WMD_K_FUSED, st);
-        wmd_fused_small_kernel<<<grid, wpb * 32, smem, st>>>(F);
+        kern<<<grid, wpb * 32, smem, st>>>(F);
         CK(cudaGetLastError());
     }
     if (!big) return WMD_OK;
@@ -986,7 +995,7 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
     IB = std::min<int64_t>(IB, 4096);
     const int64_t ldza = IB, ldlb = ldzb;
     if ((rc = B[AP_ZA].ensure((size_t)E->V * ldza * 2)) || (rc = B[AP_LB].ensure((size_t)IB * ldlb * 4)) || (rc = B[AP_KTH].ensure((size_t)IB * 4)) ||
-        (rc = B[AP_THR].ensure((size_t)IB * 4)) || (rc = B[AP_COUNTS].ensure((size_t)IB * 4)) || (rc = B[AP_OFFS].ensure((size_t)(IB + 1) * 8)) ||
+        (rc = B[AP_THR].ensure((size_t)IB * 4)) || (rc = B[AP_COUNTS].ensure((size_t)IB * kCandWarps * 4)) || (rc = B[AP_OFFS].ensure((size_t)(IB * kCandWarps + 1) * 8)) ||
         (rc = B[AP_TOPJ].ensure((size_t)IB * k * 4)) || (rc = B[AP_TOPD].ensure((size_t)IB * k * 8)) || (rc = B[AP_KCUR].ensure((size_t)IB * 4)))
         return rc;
     const size_t lb_smem = (size_t)kLbTile * kLbPitch * 4;
@@ -1023,10 +1032,10 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             cand_rows_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, lo, hi, 0, B[AP_COUNTS].as<int32_t>(), nullptr,
                                                 (int32_t)i0, nullptr, nullptr);
             CK(cudaGetLastError());
-            scan_counts_kernel<<<1, 1024, 0, st>>>(B[AP_COUNTS].as<int32_t>(), ni, B[AP_OFFS].as<int64_t>());
+            scan_counts_kernel<<<1, 1024, 0, st>>>(B[AP_COUNTS].as<int32_t>(), ni * kCandWarps, B[AP_OFFS].as<int64_t>());
             CK(cudaGetLastError());
             int64_t ncand = 0;
-            CK(cudaMemcpyAsync(&ncand, B[AP_OFFS].as<int64_t>() + ni, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&ncand, B[AP_OFFS].as<int64_t>() + (int64_t)ni * kCandWarps, 8, cudaMemcpyDeviceToHost, st));
             tm.mark(2);
             CK(cudaStreamSynchronize(st));                     // the one host round trip per round: the candidate count sizes the exact job
             if (ncand > 0) {
@@ -1127,6 +1136,8 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if ((rc = setup_fast_path(E))) return bail(rc);
         if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
         if (const char *v = getenv("WMD_SOLVE_BLOCKS")) E->solve_blocks_per_sm = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_SOLVE_C_BLOCKS")) E->solve_c_blocks = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
     if (cudaMemset(E->table, 0, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ECUDA, "memset failed"));

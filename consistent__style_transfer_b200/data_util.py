@@ -28,15 +28,10 @@ import numpy as np
 
 
 def flatten(sentences: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
-    """list of id lists -> (flat int64 ids, int64 offsets[len + 1])"""
-    n = len(sentences)
-    off = np.zeros(n + 1, np.int64)
-    if n:
-        np.cumsum(np.fromiter(map(len, sentences), dtype=np.int64, count=n), out=off[1:])
-    flat = np.empty(int(off[-1]), np.int64)
-    if flat.shape[0]:
-        flat[:] = [t for s in sentences for t in s]
-    return flat, off
+    """list of id lists -> (flat int64 ids, int64 offsets[len + 1]); both writable"""
+    from .engine import docs_to_csr                      # the C packer when it is built, numpy otherwise
+    flat, off = docs_to_csr(sentences, np.int64)
+    return (flat if flat.flags.writeable else flat.copy()), (off if off.flags.writeable else off.copy())
 
 
 def split(flat: np.ndarray, off: np.ndarray) -> List[list]:
@@ -132,23 +127,29 @@ def transfer_noise_cuda(x, p: float, pad_id: int = 0, generator=None, out_len=No
     s_sent = sent.view(-1)[order]
     s_tok = x.reshape(-1)[order]
     s_real = real.view(-1)[order]
-    # position inside the target sentence = rank among the tokens of the same sentence
-    counts = torch.zeros(B, dtype=torch.long, device=dev).scatter_add_(0, s_sent[s_real], torch.ones_like(s_sent[s_real]))
+    # position inside the target sentence = rank among the tokens of the same sentence (masks, no boolean indexing:
+    # that would read a count back to the host)
+    counts = torch.zeros(B, dtype=torch.long, device=dev).scatter_add_(0, s_sent, s_real.to(torch.long))
     start = torch.cumsum(counts, 0) - counts
     pos = torch.arange(B * L, device=dev) - start[s_sent]
     ok = s_real & (pos < W)
-    out = torch.full((B, W), pad_id, dtype=x.dtype, device=dev)
-    out[s_sent[ok], pos[ok]] = s_tok[ok]
-    return out
+    flat = torch.full((B * W + 1,), pad_id, dtype=x.dtype, device=dev)           # the last slot swallows pads / overflow
+    flat.scatter_(0, torch.where(ok, s_sent * W + pos, torch.full_like(pos, B * W)), s_tok)
+    flat[B * W] = pad_id
+    return flat[:B * W].view(B, W)
 
 
 def rand_perm_cuda(x, p: float = 0.15, pad_id: int = 0, generator=None):
-    """`rand_perm` for a padded CUDA batch: a random subset of the real token positions is permuted among itself."""
+    """`rand_perm` for a padded CUDA batch: a random subset of the real token positions is permuted among itself
+    (two sorts, no host round trip: picked positions in index order receive the picked tokens in random order, every
+    other position maps to itself)."""
     import torch
-    real = x != pad_id
-    picked = real & (torch.rand(x.shape, device=x.device, generator=generator) < p)
-    idx = torch.nonzero(picked.view(-1)).view(-1)
-    out = x.clone().view(-1)
-    if idx.numel():
-        out[idx] = out[idx[torch.randperm(idx.numel(), device=x.device, generator=generator)]]
+    n = x.numel()
+    real = (x != pad_id).view(-1)
+    picked = real & (torch.rand(n, device=x.device, generator=generator) < p)
+    idx = torch.arange(n, device=x.device, dtype=torch.float64)
+    natural = torch.argsort(torch.where(picked, idx, idx + n))
+    shuffled = torch.argsort(torch.where(picked, torch.rand(n, device=x.device, generator=generator, dtype=torch.float64), idx + 2.0))
+    out = torch.empty_like(x).view(-1)
+    out[natural] = x.reshape(-1)[shuffled]
     return out.view_as(x)
