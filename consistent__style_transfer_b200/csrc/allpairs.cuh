@@ -120,37 +120,66 @@ struct ZArgs {
     __half *Z; int64_t ldz;                   // Z[w * ldz + (j - doc0)]
 };
 
-// block = 64 words x 32 documents: a warp reads 64 consecutive halves (128 B) of one table row per token
+// block = 128 words x 32 documents: warp y owns one document, its lanes four consecutive words each (one 8-byte
+// load per token: 256 B of a table row per warp); the document's row ids are fetched once, 32 per lane, and handed
+// round by shuffles, so the loop holds no dependent global load besides the table read itself.
+__device__ __forceinline__ uint2 hmin4(uint2 a, uint2 b)
+{
+    uint2 r;
+    *reinterpret_cast<__half2 *>(&r.x) = __hmin2(*reinterpret_cast<const __half2 *>(&a.x), *reinterpret_cast<const __half2 *>(&b.x));
+    *reinterpret_cast<__half2 *>(&r.y) = __hmin2(*reinterpret_cast<const __half2 *>(&a.y), *reinterpret_cast<const __half2 *>(&b.y));
+    return r;
+}
+
 __global__ void __launch_bounds__(1024)
 z_build16_kernel(const __grid_constant__ ZArgs A)
 {
-    __shared__ __half2 tile[32][33];          // [doc][word pair]
+    __shared__ uint2 tile[32][33];            // [doc][word quad]
     const int x = threadIdx.x, y = threadIdx.y;
-    const int w0 = blockIdx.y * 64, j0 = blockIdx.x * 32;
-    const int j = j0 + y, w = w0 + 2 * x;
-    const __half inf = __ushort_as_half((unsigned short)0x7c00);
-    __half2 best = __halves2half2(inf, inf);
-    if (j < A.ndocs && w < A.V) {
+    const int w0 = blockIdx.y * 128, j0 = blockIdx.x * 32;
+    const int j = j0 + y, w = w0 + 4 * x;
+    const unsigned short infb = 0x7c00;
+    uint2 best = make_uint2(0x7c007c00u, 0x7c007c00u);
+    const bool vec = (A.V & 3) == 0;                               // rows of D16 are 8-byte aligned
+    if (j < A.ndocs) {                                             // warp-uniform (y is the warp)
         const int64_t a = A.off[A.doc0 + j];
         const int u = A.uniq[A.doc0 + j];
-        if (w + 1 < A.V && (A.V & 1) == 0) {                                 // aligned pair loads
-            for (int k = 0; k < u; ++k)
-                best = __hmin2(best, *reinterpret_cast<const __half2 *>(A.D16 + (int64_t)A.rows[a + k] * A.V + w));
-        } else {
-            for (int k = 0; k < u; ++k) {
-                const __half *r = A.D16 + (int64_t)A.rows[a + k] * A.V;
-                best = __hmin2(best, __halves2half2(r[w], w + 1 < A.V ? r[w + 1] : inf));
+        for (int k0 = 0; k0 < u; k0 += kWarp) {
+            const int mine = k0 + x < u ? A.rows[a + k0 + x] : 0;
+            const int nk = min(kWarp, u - k0);
+            const bool fast = vec && w + 3 < A.V;
+            for (int k = 0; k < nk; k += 4) {                      // four table reads in flight per lane: one at a time the loop is latency-bound
+                int rr[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) rr[c] = __shfl_sync(kFull, mine, min(k + c, nk - 1));     // a repeated row does not change a minimum
+                if (fast) {
+                    uint2 v[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[c] = __ldg(reinterpret_cast<const uint2 *>(A.D16 + (int64_t)rr[c] * A.V + w));
+                    best = hmin4(best, hmin4(hmin4(v[0], v[1]), hmin4(v[2], v[3])));
+                } else if (w < A.V) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const __half *r = A.D16 + (int64_t)rr[c] * A.V;
+                        unsigned short h[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = w + e < A.V ? __half_as_ushort(r[w + e]) : infb;
+                        best = hmin4(best, make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16)));
+                    }
+                }
             }
         }
     }
     tile[y][x] = best;
     __syncthreads();
-    // transposed write: thread (x = document, y = word pair) stores two rows of Z
-    const int jw = j0 + x, ww = w0 + 2 * y;
+    // transposed write: thread (x = document, y = word quad) stores four rows of Z
+    const int jw = j0 + x, ww = w0 + 4 * y;
     if (jw < A.ndocs && ww < A.V) {
-        const __half2 v = tile[x][y];
-        A.Z[(int64_t)ww * A.ldz + jw] = __low2half(v);
-        if (ww + 1 < A.V) A.Z[(int64_t)(ww + 1) * A.ldz + jw] = __high2half(v);
+        const uint2 v = tile[x][y];
+        const unsigned short h[4] = { (unsigned short)(v.x & 0xffffu), (unsigned short)(v.x >> 16), (unsigned short)(v.y & 0xffffu), (unsigned short)(v.y >> 16) };
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (ww + c < A.V) A.Z[(int64_t)(ww + c) * A.ldz + jw] = __ushort_as_half(h[c]);
     }
 }
 
@@ -172,6 +201,10 @@ struct LbArgs {
 
 constexpr int kLbTile = 128;
 constexpr int kLbPitch = kLbTile + 1;
+constexpr int kLbWarps = 16;
+// Shared-memory transpose without bank conflicts: element (j, i) of the 128 x 128 tile lives at row (j % 4) * 32 + j / 4,
+// column (i % 4) * 32 + i / 4 -- a lane that owns four consecutive i (or j) then touches 32 different banks per access.
+__device__ __forceinline__ int lb_swz(int t) { return (t & 3) * 32 + (t >> 2); }
 
 __device__ __forceinline__ void lb_accumulate(const int2 *list, int u, const __half *Z, int64_t ldz, int col, float (&acc)[4])
 {
@@ -186,7 +219,7 @@ __device__ __forceinline__ void lb_accumulate(const int2 *list, int u, const __h
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kLbWarps)
 lb_tile16_kernel(const __grid_constant__ LbArgs A)
 {
     extern __shared__ float l2t[];                                           // [128 corpus docs][kLbPitch] : L2(i, j) at [j][i]
@@ -195,7 +228,7 @@ lb_tile16_kernel(const __grid_constant__ LbArgs A)
     const int ib = blockIdx.x * kLbTile, jb = blockIdx.y * kLbTile;
     const float kInf = __int_as_float(0x7f800000);
     // L2(i, j): one corpus document per task, lanes along i
-    for (int t = warp; t < kLbTile; t += 8) {
+    for (int t = warp; t < kLbTile; t += kLbWarps) {
         const int j = jb + t;
         float acc[4] = { kInf, kInf, kInf, kInf };
         if (j < A.nB && A.nvalB[j] > 0) {
@@ -203,11 +236,11 @@ lb_tile16_kernel(const __grid_constant__ LbArgs A)
             lb_accumulate(A.listB + A.offB[j], A.uniqB[j], A.ZA, A.ldza, ib + 4 * lane, acc);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) l2t[t * kLbPitch + 4 * lane + c] = acc[c];
+        for (int c = 0; c < 4; ++c) l2t[lb_swz(t) * kLbPitch + c * 32 + lane] = acc[c];            // i = 4 lane + c
     }
     __syncthreads();
     // L1(i, j): one query document per task, lanes along j
-    for (int t = warp; t < kLbTile; t += 8) {
+    for (int t = warp; t < kLbTile; t += kLbWarps) {
         const int i = ib + t;
         if (i >= A.ni) break;
         float acc[4] = { kInf, kInf, kInf, kInf };
@@ -218,7 +251,7 @@ lb_tile16_kernel(const __grid_constant__ LbArgs A)
         float4 o;
         float *op = &o.x;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) op[c] = fmaxf(acc[c], l2t[(4 * lane + c) * kLbPitch + t]);     // inf if either side is empty
+        for (int c = 0; c < 4; ++c) op[c] = fmaxf(acc[c], l2t[(c * 32 + lane) * kLbPitch + lb_swz(t)]);     // j = 4 lane + c; inf if either side is empty
         *reinterpret_cast<float4 *>(A.LB + (int64_t)i * A.ldlb + jb + 4 * lane) = o;              // columns >= nB are padding
     }
 }
@@ -316,19 +349,29 @@ cand_rows_kernel(const float *LB, int64_t ldlb, int32_t n, const float *lo, cons
     const unsigned lt = (1u << lane) - 1u;
     int total = 0;
     int64_t base = fill ? offsets[(int64_t)r * kCandWarps + wid] : 0;
-    for (int jb = j0; jb < j1; jb += 128) {
+    for (int jb = j0; jb < j1; jb += 128) {                                     // lane: columns jb + 4 lane .. + 3, one 16-byte load
+        const int j = jb + 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < j1) v = __ldcs(reinterpret_cast<const float4 *>(row + j));      // rows are padded to a multiple of 128 columns
+        const float vv[4] = { v.x, v.y, v.z, v.w };
+        unsigned mine = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (j + c < j1 && vv[c] <= h && (!has_lo || vv[c] > l)) mine |= 1u << c;
+        if (!fill) { total += __popc(mine); continue; }
+        // ascending j: everything of lower lanes first, then this lane's own earlier columns
+        int before = 0, all = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int j = jb + 32 * c + lane;
-            bool take = false;
-            if (j < j1) { const float v = row[j]; take = v <= h && (!has_lo || v > l); }
-            const unsigned bal = __ballot_sync(kFull, take);
-            if (fill) {
-                if (take) { const int64_t pos = base + __popc(bal & lt); ci[pos] = row0 + r; cj[pos] = j; }
-                base += __popc(bal);
-            } else total += __popc(bal);
+            const unsigned bal = __ballot_sync(kFull, (mine >> c) & 1u);
+            before += __popc(bal & lt); all += __popc(bal);
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if ((mine >> c) & 1u) { const int64_t pos = base + before + __popc(mine & ((1u << c) - 1u)); ci[pos] = row0 + r; cj[pos] = j + c; }
+        base += all;
     }
+    if (!fill) total = __reduce_add_sync(kFull, total);
     if (!fill && lane == 0) counts[(int64_t)r * kCandWarps + wid] = total;
 }
 
