@@ -12,8 +12,9 @@ region; pairs are independent -- BASELINE north_star / SURVEY 8(e)).
 
 value  = pairs/s with the rank's slice already resident in HBM (wmd_pairs_dev), CUDA-event timed, max over ranks.
 e2e    = pairs/s through the public call on HOST buffers: N = 1 `WMDEngine.wmd_pairs` (wmd_pairs_host) on pinned
-         arrays, N > 1 `sharding.wmd_pairs_sharded(engine.wmd_pairs_torch, ...)` on the global batch + a device->host
-         read of the gathered scores; H2D of ids + offsets and D2H of scores + status inside the timed region.
+         arrays, N > 1 `sharding.wmd_pairs_sharded(engine.wmd_pairs_torch, ...)` on the global batch (every rank ends
+         with all scores on its device) + a device->host read of the rank's own slice; H2D of ids + offsets and D2H of
+         scores + status inside the timed region.
 The engine runs its default policy: the V x V word-distance table (400 MB at V = 10k) is built ONCE by the first call
 (warm-up; `table_build_ms`, `table_break_even_pairs`) and every step takes its costs from it through the fused
 warp-per-pair kernel; `without_table` is the same measurement on the direct path that recomputes every float32
@@ -337,8 +338,11 @@ def pairs_arm(ctx, cpu):
         if world == 1:
             eng.wmd_pairs(np_ids1, np_off1, np_ids2, np_off2, out=np_out, status=np_st)       # returns after the D2H of the scores
         else:
-            out, st, _ = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, np_ids1, np_off1, np_ids2, np_off2)
-            h_out.copy_(out, non_blocking=True); h_st.copy_(st, non_blocking=True)
+            # every rank ends with ALL scores on its device (the product's contract) and reads its OWN slice back:
+            # the global result reaches host memory exactly once per step
+            out, st, (a0, a1) = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, np_ids1, np_off1, np_ids2, np_off2)
+            h_out[a0:a1].copy_(out[a0:a1], non_blocking=True); h_st[a0:a1].copy_(st[a0:a1], non_blocking=True)
+            gathered["e2e_out"] = out
             torch.cuda.synchronize()
 
     def measure(label):
@@ -378,10 +382,14 @@ def pairs_arm(ctx, cpu):
         ctx.barrier()
         e2e_s = ctx.max_over_ranks(e2e_s)
         dev_scores = (gathered["out"] if world > 1 else d_out).cpu().numpy()
+        if world > 1:                                                      # the e2e arm's gathered tensor against the device arm's
+            same = bool(np.array_equal(gathered["e2e_out"].cpu().numpy(), dev_scores)) and bool(np.array_equal(np_out[lo:hi], dev_scores[lo:hi]))
+        else:
+            same = bool(np.array_equal(np_out, dev_scores))
         return {"label": label, "total_ms": total_ms, "total_ms_max": total_ms_max, "prof": prof, "prof_serial": prof_serial,
                 "stats": stats, "e2e_s": e2e_s, "first_call_s": first_s,
                 "value": n_all * a.steps / (total_ms_max / 1e3), "e2e_value": n_all * a.steps / e2e_s,
-                "same": bool(np.array_equal(np_out, dev_scores)), "scores": dev_scores}
+                "same": same, "scores": dev_scores}
 
     sampler = ClockSampler(ctx.local)
     sampler.start()
@@ -453,7 +461,9 @@ def pairs_arm(ctx, cpu):
             "clocks": clocks,
             "e2e": {"value": main["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_all * 12),
                     "timing": "perf_counter around the public call on pinned host buffers (N = 1: WMDEngine.wmd_pairs; N > 1: "
-                              "sharding.wmd_pairs_sharded + device->host read of the gathered scores), max over ranks",
+                              "sharding.wmd_pairs_sharded -- H2D of the rank's slice, kernels, NCCL gather of all scores on every "
+                              "device -- + device->host read of the rank's own slice, so the global result reaches host memory once), "
+                              "max over ranks",
                     "matches_device_path": main["same"]},
             "gpu_launches": launches,
             "roofline": roofline,

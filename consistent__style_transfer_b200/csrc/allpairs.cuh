@@ -120,51 +120,56 @@ struct ZArgs {
     __half *Z; int64_t ldz;                   // Z[w * ldz + (j - doc0)]
 };
 
-// block = 128 words x 32 documents: warp y owns one document, its lanes four consecutive words each (one 8-byte
-// load per token: 256 B of a table row per warp); the document's row ids are fetched once, 32 per lane, and handed
-// round by shuffles, so the loop holds no dependent global load besides the table read itself.
-__device__ __forceinline__ uint2 hmin4(uint2 a, uint2 b)
+// block = 256 words x 32 documents: warp y owns one document, its lanes eight consecutive words each (one 16-byte load
+// per token: 512 B of a table row per warp); the document's row ids are fetched once, 32 per lane, and handed round by
+// shuffles, four table reads in flight per lane.  ncu (profiles/README.md): the kernel is bound by instruction issue,
+// not by the L2 -- eight words per load instead of four halved its instructions; staging the table's hot rows or whole
+// column strips in shared memory (both tried) only moved the limit to the shared-memory pipe.
+__device__ __forceinline__ uint4 hmin8(uint4 a, uint4 b)
 {
-    uint2 r;
+    uint4 r;
     *reinterpret_cast<__half2 *>(&r.x) = __hmin2(*reinterpret_cast<const __half2 *>(&a.x), *reinterpret_cast<const __half2 *>(&b.x));
     *reinterpret_cast<__half2 *>(&r.y) = __hmin2(*reinterpret_cast<const __half2 *>(&a.y), *reinterpret_cast<const __half2 *>(&b.y));
+    *reinterpret_cast<__half2 *>(&r.z) = __hmin2(*reinterpret_cast<const __half2 *>(&a.z), *reinterpret_cast<const __half2 *>(&b.z));
+    *reinterpret_cast<__half2 *>(&r.w) = __hmin2(*reinterpret_cast<const __half2 *>(&a.w), *reinterpret_cast<const __half2 *>(&b.w));
     return r;
 }
+
+constexpr int kZWords = 256;                  // words per block
 
 __global__ void __launch_bounds__(1024)
 z_build16_kernel(const __grid_constant__ ZArgs A)
 {
-    __shared__ uint2 tile[32][33];            // [doc][word quad]
+    __shared__ uint4 tile[32][33];            // [doc][word octet]
     const int x = threadIdx.x, y = threadIdx.y;
-    const int w0 = blockIdx.y * 128, j0 = blockIdx.x * 32;
-    const int j = j0 + y, w = w0 + 4 * x;
+    const int w0 = blockIdx.y * kZWords, j0 = blockIdx.x * 32;
+    const int j = j0 + y, w = w0 + 8 * x;
     const unsigned short infb = 0x7c00;
-    uint2 best = make_uint2(0x7c007c00u, 0x7c007c00u);
-    const bool vec = (A.V & 3) == 0;                               // rows of D16 are 8-byte aligned
+    uint4 best = make_uint4(0x7c007c00u, 0x7c007c00u, 0x7c007c00u, 0x7c007c00u);
+    const bool fast = (A.V & 7) == 0 && w + 7 < A.V;               // rows of D16 are 16-byte aligned and this lane's octet is whole
     if (j < A.ndocs) {                                             // warp-uniform (y is the warp)
         const int64_t a = A.off[A.doc0 + j];
         const int u = A.uniq[A.doc0 + j];
         for (int k0 = 0; k0 < u; k0 += kWarp) {
             const int mine = k0 + x < u ? A.rows[a + k0 + x] : 0;
             const int nk = min(kWarp, u - k0);
-            const bool fast = vec && w + 3 < A.V;
-            for (int k = 0; k < nk; k += 4) {                      // four table reads in flight per lane: one at a time the loop is latency-bound
+            for (int k = 0; k < nk; k += 4) {                      // four table reads in flight per lane: one at a time the loop waits on each
                 int rr[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) rr[c] = __shfl_sync(kFull, mine, min(k + c, nk - 1));     // a repeated row does not change a minimum
                 if (fast) {
-                    uint2 v[4];
+                    uint4 v[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) v[c] = __ldg(reinterpret_cast<const uint2 *>(A.D16 + (int64_t)rr[c] * A.V + w));
-                    best = hmin4(best, hmin4(hmin4(v[0], v[1]), hmin4(v[2], v[3])));
+                    for (int c = 0; c < 4; ++c) v[c] = __ldg(reinterpret_cast<const uint4 *>(A.D16 + (int64_t)rr[c] * A.V + w));
+                    best = hmin8(best, hmin8(hmin8(v[0], v[1]), hmin8(v[2], v[3])));
                 } else if (w < A.V) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const __half *r = A.D16 + (int64_t)rr[c] * A.V;
-                        unsigned short h[4];
+                        unsigned h[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = w + e < A.V ? __half_as_ushort(r[w + e]) : infb;
-                        best = hmin4(best, make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16)));
+                        for (int e = 0; e < 8; ++e) h[e] = w + e < A.V ? __half_as_ushort(r[w + e]) : infb;
+                        best = hmin8(best, make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16)));
                     }
                 }
             }
@@ -172,14 +177,14 @@ z_build16_kernel(const __grid_constant__ ZArgs A)
     }
     tile[y][x] = best;
     __syncthreads();
-    // transposed write: thread (x = document, y = word quad) stores four rows of Z
-    const int jw = j0 + x, ww = w0 + 4 * y;
+    // transposed write: thread (x = document, y = word octet) stores eight rows of Z
+    const int jw = j0 + x, ww = w0 + 8 * y;
     if (jw < A.ndocs && ww < A.V) {
-        const uint2 v = tile[x][y];
-        const unsigned short h[4] = { (unsigned short)(v.x & 0xffffu), (unsigned short)(v.x >> 16), (unsigned short)(v.y & 0xffffu), (unsigned short)(v.y >> 16) };
+        const uint4 v = tile[x][y];
+        const unsigned q[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (ww + c < A.V) A.Z[(int64_t)(ww + c) * A.ldz + jw] = __ushort_as_half(h[c]);
+        for (int c = 0; c < 8; ++c)
+            if (ww + c < A.V) A.Z[(int64_t)(ww + c) * A.ldz + jw] = __ushort_as_half((unsigned short)((q[c >> 1] >> (16 * (c & 1))) & 0xffffu));
     }
 }
 

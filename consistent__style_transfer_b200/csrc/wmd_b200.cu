@@ -984,7 +984,7 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
         ZArgs Z;
         Z.D16 = E->dtab16; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSB].as<int32_t>(); Z.off = dOffB; Z.uniq = B[AP_UNIQB].as<int32_t>();
         Z.doc0 = 0; Z.ndocs = (int32_t)nB; Z.Z = B[AP_ZB].as<__half>(); Z.ldz = ldzb;
-        dim3 grid((unsigned)((nB + 31) / 32), (unsigned)((E->V + 127) / 128));
+        dim3 grid((unsigned)((nB + 31) / 32), (unsigned)((E->V + kZWords - 1) / kZWords));
         z_build16_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
         CK(cudaGetLastError());
     }
@@ -1008,7 +1008,7 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             ZArgs Z;
             Z.D16 = E->dtab16; Z.V = (int32_t)E->V; Z.rows = B[AP_ROWSA].as<int32_t>(); Z.off = dOffA; Z.uniq = B[AP_UNIQA].as<int32_t>();
             Z.doc0 = i0; Z.ndocs = ni; Z.Z = B[AP_ZA].as<__half>(); Z.ldz = ldza;
-            dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((E->V + 127) / 128));
+            dim3 grid((unsigned)((ni + 31) / 32), (unsigned)((E->V + kZWords - 1) / kZWords));
             z_build16_kernel<<<grid, dim3(32, 32), 0, st>>>(Z);
             CK(cudaGetLastError());
             LbArgs L;
