@@ -15,8 +15,11 @@ constexpr int kIntInf = 0x3fffffff;      // "infinite" tentative distance (sums 
 constexpr int kClsNone = 0;              // nothing to do (early-out already written)
 constexpr int kClsA = 1;                 // residual rows <= 32 and columns (incl. dummy) <= 32
 constexpr int kClsB = 2;                 // <= 64 / <= 64
-constexpr int kClsC = 3;                 // <= 128 / <= 160
-constexpr int kClsD = 4;                 // anything up to 256 x 257
+constexpr int kClsC = 3;                 // <= 96 / <= 96      (multi-word solver <3, 3>)
+constexpr int kClsD = 4;                 // <= 128 / <= 160    (<4, 5>)
+constexpr int kClsE = 5;                 // <= 192 / <= 192    (<6, 6>)
+constexpr int kClsF = 6;                 // anything up to 256 x 257 (<8, 9>)
+constexpr int kClsLast = kClsF;
 constexpr int kMetaSwap = 8;             // doc2 is the heavier (supplying) side
 
 // One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).

@@ -344,14 +344,16 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Classes B (<= 64 x 64), C (<= 128 x 160) and D (<= 256 x 257): the class-A design with KR row words and KC column
+// Classes B (<= 64 x 64) and C .. F (<= 96 x 96, 128 x 160, 192 x 192, 256 x 257): the class-A design with KR row words and KC column
 // words.  Lane L is rows L + 32k (k < KR) and columns L + 32k (k < KC); duals, tentative distances and
 // tree predecessors stay in registers, the tree / used-column sets are KR / KC warp-uniform words,
 // and cmask[j][KR] (shared memory) says which rows ship into column j.  The flow matrix is only ever
 // touched along augmenting paths and where cmask has a bit, so it lives in global scratch and is never
 // cleared (a cell is written, not added to, when its bit is off).  Costs: shared memory (class B) or
-// L2-resident global scratch (classes C and D; every selection step walks all KC column words and every new tree row
-// all KR row words, so a 100 x 100 problem runs ~2x faster in the <4, 5> instance than in <8, 9>).  The previous version kept dense cost AND flow per warp in
+// L2-resident global scratch (classes C .. F).  Every selection step walks all KC column words and every new tree row
+// all KR row words, and the register arrays grow with both, so each size class has its own instance -- <3, 3>, <4, 5>,
+// <6, 6>, <8, 9> -- its own launch, register count and scratch pitch: 187 x 188 problems (256-token documents) run 2.2x
+// faster in <6, 6> than they did in <8, 9>, 103 x 104 ones 2.3x faster in <4, 5>.  The previous version kept dense cost AND flow per warp in
 // shared memory (35 kB: 4 warps per SM) and found the rows of a saturated column by scanning a flow
 // column with dependent loads; profiles/README.md has the before / after.
 // ------------------------------------------------------------------------------------------------

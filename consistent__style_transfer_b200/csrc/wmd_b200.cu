@@ -88,8 +88,8 @@ struct ProfRec { int kind; cudaEvent_t a, b; };
 
 // unsigned slots of Workspace::counters
 constexpr size_t kCounterBytes = 128;
-constexpr int kCtrFused = 6;                    // fused kernel's work-claim counter (slots 1..4: the solver classes)
-constexpr int kCtrNBig = 7;                     // length of Workspace::biglist
+constexpr int kCtrFused = 10;                   // fused kernel's work-claim counter (slots 1..6: the solver classes)
+constexpr int kCtrNBig = 11;                    // length of Workspace::biglist
 constexpr int kCtrCost = 8;                     // general cost kernel's claim counter
 constexpr int kCtrStages = 9;                   // planned stages of the fast cost path
 constexpr int kCtrDmax = 12;                    // largest entry of the word-distance table (float bits)
@@ -126,6 +126,7 @@ struct wmd_engine {
     void *pin_in = nullptr, *pin_out = nullptr;  // wmd_pairs_submit / wmd_pairs_wait: handle-owned pinned staging
     size_t pin_in_cap = 0, pin_out_cap = 0;
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
+    bool b_global = true;                        // class B costs in L2-resident global scratch (24 instead of 12 warps per SM: 64-token pairs 28 -> 19 ms per 2^18); WMD_B_GLOBAL=0: shared memory
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
@@ -134,7 +135,6 @@ struct wmd_engine {
     unsigned long long *stats = nullptr;        // device [6]
     bool profiling = false;
     int solve_blocks_per_sm = 8;                 // K3 grid cap per SM (WMD_SOLVE_BLOCKS): fewer leaves room for a co-resident K2b
-    int solve_c_blocks = 4;                      // class C (<4, 5>) blocks of 4 warps per SM (WMD_SOLVE_C_BLOCKS)
     int fast_stage_cap = kFastMaxStages;         // K2b ring depth cap (WMD_FAST_S)
     int slot_mask = 1;                           // 0 (WMD_SERIAL=1): every chunk on one stream, for clean per-kernel timings
     std::vector<ProfRec> prof;
@@ -370,22 +370,46 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
     return WMD_OK;
 }
 
-// K3 launches of one chunk: the class-A / B / C solvers over all pairs of the chunk, or (list mode) over the pairs the
+// K3 launches of one chunk: one launch per solver class over all pairs of the chunk, or (list mode) over the pairs the
 // fused kernel left behind.  gather: costs come from the word-distance table instead of cost tiles.
+struct SolverClass { int cls, rows, cols, min_ml; };            // capacity of the class and the shortest longer side that can produce it
+constexpr SolverClass kSolverClasses[] = {
+    { kClsA, 32, 32, 1 },  { kClsB, 64, 64, 32 },  { kClsC, 96, 96, 64 },  { kClsD, 128, 160, 96 },
+    { kClsE, 192, 192, 129 },  { kClsF, kMaxDocLen, kMaxDocLen + 1, 192 },
+};
+
+template <class K>
+int launch_multi_solver(wmd_engine *E, Workspace &W, cudaStream_t st, K kernel, SolveArgs &S, size_t per_warp, int32_t Bc)
+{
+    int rc;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, wpb * 32, smem));
+    if (nb < 1) return fail(WMD_ECUDA, "solver class %d cannot be resident", S.cls);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + wpb - 1) / wpb, (int64_t)E->sm_count * nb));
+    // per warp: flow (class B; its costs sit in shared memory), cost + flow (larger classes)
+    if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
+    S.scratch = W.scratch.as<int32_t>();
+    Prof pr(E, WMD_K_SOLVE, st);
+    kernel<<<grid, wpb * 32, smem, st>>>(S);
+    CK(cudaGetLastError());
+    return WMD_OK;
+}
+
 int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, const DocSide &s2, int64_t p0, int32_t Bc, int ML,
                    const PairWork &pw, const float *tiles, int64_t tile_stride, const ChunkOut &O, const int32_t *list,
                    const unsigned int *nlist, bool gather)
 {
     int rc;
-    for (int cls = kClsA; cls <= kClsD; ++cls) {
-        if (cls == kClsB && ML < 32) continue;       // nc = n + 1 > 32 needs a side with >= 32 tokens
-        if (cls == kClsC && ML < 64) continue;
-        if (cls == kClsD && ML <= 128) continue;     // m > 128 or nc > 160
+    for (const SolverClass &C : kSolverClasses) {
+        if (ML < C.min_ml) continue;                  // no document of the chunk is long enough for a residual problem of this class
+        const int cls = C.cls;
         SolveArgs S;
         S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
-        const int capr = cls == kClsA ? 32 : cls == kClsB ? 64 : cls == kClsC ? 128 : kMaxDocLen;
-        const int capc = cls == kClsA ? 32 : cls == kClsB ? 64 : cls == kClsC ? 160 : kMaxDocLen + 1;
-        S.mr = std::min(capr, ML); S.mc = std::min(capc, ML + 1);
+        S.mr = std::min(C.rows, ML); S.mc = std::min(C.cols, ML + 1);
         if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
         S.ldc = S.mc | 1;
         S.use_global = cls >= kClsC;
@@ -395,44 +419,36 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         S.out = O.out; S.status = O.status;
         S.list = list; S.nlist = nlist;
         S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
-        const bool multi = cls != kClsA;
-        int wpb = 8;
-        size_t per_warp = cls == kClsA ? solve_small_smem_per_warp(S.mr, S.mc, S.ldc)
-                        : cls == kClsB ? solve_multi_smem_per_warp<2, 2>(S.mr, S.mc, S.ldc, false)
-                        : cls == kClsC ? solve_multi_smem_per_warp<4, 5>(S.mr, S.mc, S.ldc, true)
-                                       : solve_multi_smem_per_warp<8, 9>(S.mr, S.mc, S.ldc, true);
-        int blocks_per_sm = E->solve_blocks_per_sm;
-        if (cls == kClsA) { wpb = 4; blocks_per_sm *= 2; }                                // __launch_bounds__(128, 9)
-        if (cls == kClsB) { wpb = 4; blocks_per_sm = std::max(1, std::min<int>(8, (int)((220 * 1024) / (per_warp * wpb + 1024)))); }
-        if (cls == kClsC) { wpb = 4; blocks_per_sm = E->solve_c_blocks; }
-        if (cls == kClsD) { wpb = 4; blocks_per_sm = 3; }                                 // 168 registers: 3 blocks of 4 warps per SM
-        while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
-        const size_t smem = per_warp * wpb;
-        const int ppw = multi ? 1 : 8;                                                    // pairs per warp below which the grid shrinks
-        int grid = (int)std::min<int64_t>(((int64_t)Bc + ppw * wpb - 1) / (ppw * wpb), (int64_t)E->sm_count * blocks_per_sm);
-        grid = std::max(grid, 1);
         S.scratch = nullptr;
-        if (multi) {
-            // per warp: flow (class B; its costs sit in shared memory), cost + flow (class C)
-            if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
-            S.scratch = W.scratch.as<int32_t>();
+        if (cls == kClsA) {
+            const int wpb = 4;
+            const size_t smem = solve_small_smem_per_warp(S.mr, S.mc, S.ldc) * wpb;
+            const int blocks_per_sm = E->solve_blocks_per_sm * 2;                         // __launch_bounds__(128, 9)
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * blocks_per_sm));
+            Prof pr(E, WMD_K_SOLVE, st);
+            if (gather) {
+                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                emd_solve_small_kernel<true><<<grid, wpb * 32, smem, st>>>(S);
+            } else {
+                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                emd_solve_small_kernel<false><<<grid, wpb * 32, smem, st>>>(S);
+            }
+            CK(cudaGetLastError());
+            continue;
         }
-        Prof pr(E, WMD_K_SOLVE, st);
-#define WMD_LAUNCH_SOLVER(KERNEL)                                                                                        \
-        do {                                                                                                             \
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            KERNEL<<<grid, wpb * 32, smem, st>>>(S);                                                                     \
-        } while (0)
-        if (cls == kClsA) { if (gather) WMD_LAUNCH_SOLVER(emd_solve_small_kernel<true>); else WMD_LAUNCH_SOLVER(emd_solve_small_kernel<false>); }
-        else if (cls == kClsB) {
-            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<2, 2, false, false>));
-        } else if (cls == kClsC) {
-            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<4, 5, true, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<4, 5, true, false>));
-        } else {
-            if (gather) WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, true>)); else WMD_LAUNCH_SOLVER((emd_solve_multi_kernel<8, 9, true, false>));
+#define WMD_MULTI(KR, KC, GC)                                                                                                        \
+        (gather ? launch_multi_solver(E, W, st, emd_solve_multi_kernel<KR, KC, GC, true>, S, solve_multi_smem_per_warp<KR, KC>(S.mr, S.mc, S.ldc, GC), Bc) \
+                : launch_multi_solver(E, W, st, emd_solve_multi_kernel<KR, KC, GC, false>, S, solve_multi_smem_per_warp<KR, KC>(S.mr, S.mc, S.ldc, GC), Bc))
+        if (cls == kClsB) {
+            if (E->b_global) { S.use_global = 1; rc = WMD_MULTI(2, 2, true); }
+            else rc = WMD_MULTI(2, 2, false);
         }
-#undef WMD_LAUNCH_SOLVER
-        CK(cudaGetLastError());
+        else if (cls == kClsC) rc = WMD_MULTI(3, 3, true);
+        else if (cls == kClsD) rc = WMD_MULTI(4, 5, true);
+        else if (cls == kClsE) rc = WMD_MULTI(6, 6, true);
+        else rc = WMD_MULTI(8, 9, true);
+#undef WMD_MULTI
+        if (rc) return rc;
     }
     return WMD_OK;
 }
@@ -1136,7 +1152,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if ((rc = setup_fast_path(E))) return bail(rc);
         if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
         if (const char *v = getenv("WMD_SOLVE_BLOCKS")) E->solve_blocks_per_sm = std::max(1, atoi(v));
-        if (const char *v = getenv("WMD_SOLVE_C_BLOCKS")) E->solve_c_blocks = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_B_GLOBAL")) E->b_global = atoi(v) != 0;
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
