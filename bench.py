@@ -494,6 +494,7 @@ def allpairs_arm(ctx, steps=1):
     a, torch, eng, dev, world, rank = ctx.a, ctx.torch, ctx.eng, ctx.dev, ctx.world, ctx.rank
     dist = ctx.dist
     ids, off, _, _ = workload.make_pairs(a.docs, a.shape, "independent", V=a.vocab, seed=1)
+    ids = torch.from_numpy(ids).pin_memory().numpy(); off = torch.from_numpy(off).pin_memory().numpy()   # pinned host documents
     N, k = a.docs, a.topk
     blocks = sharding.row_blocks(N, world)
     r0, r1 = int(blocks[rank]), int(blocks[rank + 1])

@@ -126,6 +126,7 @@ struct wmd_engine {
     void *pin_in = nullptr, *pin_out = nullptr;  // wmd_pairs_submit / wmd_pairs_wait: handle-owned pinned staging
     size_t pin_in_cap = 0, pin_out_cap = 0;
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
+    int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
     bool b_global = true;                        // class B costs in L2-resident global scratch (24 instead of 12 warps per SM: 64-token pairs 28 -> 19 ms per 2^18); WMD_B_GLOBAL=0: shared memory
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
@@ -1007,13 +1008,29 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
     tm.mark(1);
 
     // ---- query blocks ---------------------------------------------------------------------------------
-    int64_t IB = std::min<int64_t>((nR + kLbTile - 1) / kLbTile * kLbTile, std::max<int64_t>(kLbTile, (int64_t)(1ll << 29) / std::max<int64_t>(ldzb, 1) / kLbTile * kLbTile));
-    IB = std::min<int64_t>(IB, 4096);
+    // Query rows per block: as many as a bound matrix of <= 8 GiB (and <= a quarter of the free memory) holds, at most
+    // 16 384, and all blocks of a call equally large -- every block costs two host round trips (its candidate counts) and
+    // a tail per kernel, so a rank of an 8-GPU job (12 500 rows of 100 000) runs as ONE block.
+    int64_t IB;
+    {
+        size_t freeb = 0, totalb = 0;
+        CK(cudaMemGetInfo(&freeb, &totalb));
+        const size_t budget = std::min<size_t>((size_t)8 << 30, (freeb + B[AP_LB].cap) / 4);
+        int64_t cap = std::max<int64_t>(kLbTile, (int64_t)(budget / ((size_t)ldzb * 4)) / kLbTile * kLbTile);
+        cap = std::min<int64_t>(cap, 16384);
+        if (const char *v = getenv("WMD_AP_BLOCK")) cap = std::max<int64_t>(kLbTile, std::min<int64_t>(cap, atoi(v) / kLbTile * kLbTile));
+        const int64_t nblocks = (nR + cap - 1) / cap;
+        IB = ((nR + nblocks - 1) / nblocks + kLbTile - 1) / kLbTile * kLbTile;
+    }
     const int64_t ldza = IB, ldlb = ldzb;
     if ((rc = B[AP_ZA].ensure((size_t)E->V * ldza * 2)) || (rc = B[AP_LB].ensure((size_t)IB * ldlb * 4)) || (rc = B[AP_KTH].ensure((size_t)IB * 4)) ||
         (rc = B[AP_THR].ensure((size_t)IB * 4)) || (rc = B[AP_COUNTS].ensure((size_t)IB * kCandWarps * 4)) || (rc = B[AP_OFFS].ensure((size_t)(IB * kCandWarps + 1) * 8)) ||
         (rc = B[AP_TOPJ].ensure((size_t)IB * k * 4)) || (rc = B[AP_TOPD].ensure((size_t)IB * k * 8)) || (rc = B[AP_KCUR].ensure((size_t)IB * 4)))
         return rc;
+    // Round 1 solves the k1 = ap_r1_mult * k documents with the smallest bounds, not just k: the k-th exact distance among
+    // more candidates is a tighter threshold for round 2 (k1 = k: 273 exact solves per row of the 100k x 100k job; see
+    // profiles/README.md for the sweep).
+    const int32_t k1 = (int32_t)std::min<int64_t>(nB, std::min<int64_t>(256, (int64_t)E->ap_r1_mult * k));
     const size_t lb_smem = (size_t)kLbTile * kLbPitch * 4;
     CK(cudaFuncSetAttribute(lb_tile16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem));
     const cudaMemcpyKind back = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -1040,7 +1057,7 @@ int run_allpairs(wmd_engine *E, const int32_t *idsA, const int64_t *offA, int64_
             st_local[0] += (int64_t)ni * nB;
         }
         CK(cudaMemsetAsync(B[AP_KCUR].p, 0, (size_t)ni * 4, st));
-        row_kth_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, k, B[AP_KTH].as<float>());
+        row_kth_kernel<<<ni, 256, 0, st>>>(B[AP_LB].as<float>(), ldlb, (int32_t)nB, k1, B[AP_KTH].as<float>());
         CK(cudaGetLastError());
         for (int round = 0; round < 2; ++round) {
             const float *lo = round == 0 ? nullptr : B[AP_KTH].as<float>();
@@ -1152,6 +1169,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if ((rc = setup_fast_path(E))) return bail(rc);
         if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
         if (const char *v = getenv("WMD_SOLVE_BLOCKS")) E->solve_blocks_per_sm = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
         if (const char *v = getenv("WMD_B_GLOBAL")) E->b_global = atoi(v) != 0;
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
