@@ -600,9 +600,13 @@ bool takes_fused(const wmd_engine *E, bool solve, bool rwmd, int mode)
     return E->use_dtab && E->dtab && solve && !rwmd && mode == WMD_MODE_PYEMD;
 }
 
-int64_t chunk_pairs(int ml1, int ml2, bool fused)
+// Pairs per chunk.  Direct path: what 768 MB of cost tiles hold (at most 65 536: the tile descriptors carry 16-bit pair
+// numbers).  Table mode has no tiles: a host job still goes in chunks of 65 536 so that the copies of one chunk overlap
+// the kernels of another; a device job takes up to 2^20 pairs per launch of the persistent fused kernel -- one tail per
+// million pairs instead of sixteen.
+int64_t chunk_pairs(int ml1, int ml2, bool fused, bool host_job = true)
 {
-    if (fused) return 65536;
+    if (fused) return host_job ? 65536 : (1 << 20);
     const int64_t tile = (int64_t)std::max(ml1, 1) * std::max(ml2, 1) * 4;
     int64_t c = (int64_t)(768ll << 20) / tile;
     c = std::min<int64_t>(c, 65536);
@@ -772,7 +776,8 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_join[0], E->streams[0]));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_join[0], 0));        // stats reset precedes both streams' kernels
-    const int64_t CH = chunk_pairs(ml1, ml2, takes_fused(E, O0.solve, O0.rwmd, O0.mode));
+    int64_t CH = chunk_pairs(ml1, ml2, takes_fused(E, O0.solve, O0.rwmd, O0.mode), false);
+    if (const char *v = getenv("WMD_DEV_CHUNK")) CH = std::max<int64_t>(1024, std::min<int64_t>(CH, atoll(v)));
     int slot = 0;
     for (int64_t c0 = 0; c0 < npairs; c0 += CH, slot = (slot ^ 1) & E->slot_mask) {
         const int32_t Bc = (int32_t)std::min<int64_t>(CH, npairs - c0);
