@@ -119,6 +119,7 @@ struct wmd_engine {
     float *dtab = nullptr;
     __half *dtab16 = nullptr;                    // all-pairs mode: the table rounded down to half precision (bounds only)
     bool use_dtab = false;                       // pair path takes its costs from dtab (default policy: on when the table fits dtab_budget)
+    bool dtab_forced = false;                    // the caller asked for the table (wmd_set_distance_table(1), WMD_DTAB=1): failing to build it is an error
     float dmax = 0.f;
     size_t dtab_budget = 0;                      // bytes the table may take for the default policy to switch it on
     double dtab_build_ms = 0.0;                  // wall time of the one-off build
@@ -604,6 +605,16 @@ bool takes_fused(const wmd_engine *E, bool solve, bool rwmd, int mode)
 // numbers).  Table mode has no tiles: a host job still goes in chunks of 65 536 so that the copies of one chunk overlap
 // the kernels of another; a device job takes up to 2^20 pairs per launch of the persistent fused kernel -- one tail per
 // million pairs instead of sixteen.
+// First scoring call of a handle whose policy wants the table.  Under the default policy a table that cannot be built
+// (memory taken since wmd_create) is not an error: the handle falls back to the direct path for good.
+int lazy_dtab(wmd_engine *E)
+{
+    if (!E->use_dtab || E->dtab) return WMD_OK;
+    const int rc = ensure_dtab(E, E->streams[0]);
+    if (rc == WMD_ENOMEM && !E->dtab_forced) { E->use_dtab = false; return WMD_OK; }
+    return rc;
+}
+
 int64_t chunk_pairs(int ml1, int ml2, bool fused, bool host_job = true)
 {
     if (fused) return host_job ? 65536 : (1 << 20);
@@ -657,7 +668,7 @@ struct HostJob {
 int enqueue_host_job(wmd_engine *E, const HostJob &J)
 {
     int rc;
-    if (E->use_dtab && !E->dtab && (rc = ensure_dtab(E, E->streams[0]))) return rc;      // first call: build the word-distance table
+    if ((rc = lazy_dtab(E))) return rc;                          // first call: build the word-distance table
     if ((rc = reset_stats(E, E->streams[0]))) return rc;
     CK(cudaEventRecord(E->ev_fork, E->streams[0]));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
@@ -769,7 +780,7 @@ int run_dev_job(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t tot
     if (ml1 < 0 || ml2 < 0 || ml1 > WMD_MAX_DOC_LEN || ml2 > WMD_MAX_DOC_LEN)
         return fail(WMD_EINVAL, "max_len must be within [0, %d]", WMD_MAX_DOC_LEN);
     ml1 = std::max(ml1, 1); ml2 = std::max(ml2, 1);
-    if (E->use_dtab && !E->dtab && (rc = ensure_dtab(E, E->streams[0]))) return rc;      // first call only (host-synchronous once)
+    if ((rc = lazy_dtab(E))) return rc;                          // first call only (host-synchronous once)
     CK(cudaEventRecord(E->ev_fork, us));
     CK(cudaStreamWaitEvent(E->streams[0], E->ev_fork, 0));
     CK(cudaStreamWaitEvent(E->streams[1], E->ev_fork, 0));
@@ -1204,7 +1215,7 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         E->dtab_budget = std::min<size_t>((size_t)4 << 30, freeb / 4);
         if (const char *v = getenv("WMD_DTAB_BUDGET_MB")) E->dtab_budget = (size_t)std::max(0, atoi(v)) << 20;
         E->use_dtab = (size_t)V * (size_t)V * 4 <= E->dtab_budget;
-        if (const char *v = getenv("WMD_DTAB")) E->use_dtab = atoi(v) != 0;
+        if (const char *v = getenv("WMD_DTAB")) { E->use_dtab = atoi(v) != 0; E->dtab_forced = E->use_dtab; }
     }
     *out = E;
     return WMD_OK;
@@ -1594,11 +1605,12 @@ int wmd_set_serial(wmd_handle E, int32_t enabled)
 int wmd_set_distance_table(wmd_handle E, int32_t enabled)
 {
     if (!E) return fail(WMD_EINVAL, "null handle");
-    if (!enabled) { E->use_dtab = false; return WMD_OK; }
+    if (!enabled) { E->use_dtab = false; E->dtab_forced = false; return WMD_OK; }
     int rc;
     if ((rc = set_device(E))) return rc;
+    if (E->pending_pairs >= 0) return fail(WMD_EINVAL, "a submitted job is still in flight: call wmd_pairs_wait first");
     if ((rc = ensure_dtab(E, E->streams[0]))) return rc;
-    E->use_dtab = true;
+    E->use_dtab = true; E->dtab_forced = true;
     return WMD_OK;
 }
 

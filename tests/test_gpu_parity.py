@@ -359,3 +359,24 @@ def test_async_and_device_forms_match_the_host_entries(eng_mod, oracle):
     est2, _ = e.workspace_bytes(70000, 256, 256)
     assert est2 > est
     e.close()
+
+
+def test_distance_table_policy_follows_the_budget(eng_mod, monkeypatch):
+    """Default policy: table on when V * V * 4 bytes fit the budget, direct path otherwise; same bits either way."""
+    V = 1500
+    table = workload.make_table(V, 64, seed=5)
+    ids1, off1, ids2, off2 = workload.make_pairs(2000, "yelp", "noised", V=V, seed=41)
+    e = eng_mod.WMDEngine(table)
+    info = e.distance_table_info()
+    assert info["enabled"] and not info["resident"] and info["bytes"] == V * V * 4     # built by the first scoring call
+    a, sa = e.wmd_pairs(ids1, off1, ids2, off2)
+    info = e.distance_table_info()
+    assert info["resident"] and info["build_ms"] > 0
+    e.close()
+    monkeypatch.setenv("WMD_DTAB_BUDGET_MB", "1")                                       # 9 MB table, 1 MB budget
+    e = eng_mod.WMDEngine(table)
+    assert not e.distance_table_info()["enabled"]
+    b, sb = e.wmd_pairs(ids1, off1, ids2, off2)
+    assert not e.distance_table_info()["resident"]
+    assert a.tobytes() == b.tobytes() and np.array_equal(sa, sb)
+    e.close()
