@@ -122,8 +122,42 @@ __device__ __forceinline__ long long transport_solve_small(int m, int nc, int ld
     __syncwarp();
     const bool iscol = lane < nc;
     const unsigned lbit = 1u << lane;
+    // Start from reduced costs instead of zero duals (the Hungarian method's row and column reduction): u_r = the row's
+    // cheapest arc, v_c = what is left of the column's cheapest.  Every row then owns a tight arc, and one greedy pass ships
+    // along tight arcs into columns that still have a deficit -- any flow on tight arcs under feasible duals is a valid
+    // state of the primal-dual method, and the optimum it ends in is the same integer.  On Yelp-shape pairs this replaces
+    // 6.7 of 14.5 searches and 11 of 46 column selections per pair by ~25 instructions per row (tools/solver_model.py).
+    int srem = supply;                                           // supply still to ship (lane = row); `supply` stays as handed in
+    {
+        if (lane < m) {
+            int best = kIntInf;
+            for (int c = 0; c < nc; ++c) best = min(best, lds32(cost + lane * ld4 + 4u * c));
+            u = best;
+        }
+        int best = kIntInf;
+        for (int r = 0; r < m; ++r) {
+            const int ur = __shfl_sync(kFull, u, r);
+            if (iscol) best = min(best, lds32(cost + r * ld4 + lane4) - ur);
+        }
+        if (iscol) v = best;
+        for (int r = 0; r < m; ++r) {
+            const int ur = __shfl_sync(kFull, u, r), sr = __shfl_sync(kFull, srem, r);
+            const bool open = iscol && deficit > 0 && lds32(cost + r * ld4 + lane4) - ur - v == 0;
+            const unsigned cand = __ballot_sync(kFull, open);
+            if (cand == 0 || sr == 0) continue;
+            const int j = __ffs(cand) - 1;
+            const int amt = min(sr, __shfl_sync(kFull, deficit, j));
+            if (lane == j) {
+                sts32(flow + r * ld4 + lane4, amt);
+                sts32(cmask + lane4, lds32(cmask + lane4) | (1u << r));
+                deficit -= amt;
+            }
+            if (lane == r) srem -= amt;
+        }
+        __syncwarp();
+    }
     for (int r = 0; r < m; ++r) {
-        int sup = __shfl_sync(kFull, supply, r);
+        int sup = __shfl_sync(kFull, srem, r);
         while (sup > 0) {
             unsigned used = 0, tree = 1u << r;
             int rdist = 0, rpred = -1;
