@@ -60,9 +60,12 @@ def test_search_variants_reach_the_exact_optimum(oracle, n, maxcount, dim):
             continue
         C, s, t = prob
         flipped = (C.T.copy(), t.copy(), s.copy())
-        for name, p, cont in (("rows = supplying side", (C, s, t), False), ("rows = other side", flipped, False),
-                              ("supplying side, searches continue", (C, s, t), True), ("other side, searches continue", flipped, True)):
-            got, counts = solver_model.solve(*p, cont)
+        for name, p, cont, red in (("rows = supplying side", (C, s, t), False, False), ("rows = other side", flipped, False, False),
+                                   ("supplying side, searches continue", (C, s, t), True, False),
+                                   ("other side, searches continue", flipped, True, False),
+                                   ("supplying side, reduced-cost start + greedy pass", (C, s, t), True, True),
+                                   ("other side, reduced-cost start + greedy pass", flipped, True, True)):
+            got, counts = solver_model.solve(*p, cont, red)
             assert got == want, (name, n, got, want)
         checked += 1
     assert checked > 0

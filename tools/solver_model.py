@@ -7,8 +7,9 @@ before the orientation change), so a variant can be judged without GPU time.
 
     python tools/solver_model.py [pairs]
 
-Variants reported: rows = supplying side (the original), rows = the side with more nodes (built), and the latter
-with searches continuing after intact multi-hop augmentations (built).  Every variant must return the same optimum.
+Variants reported: rows = supplying side (the original), rows = the side with more nodes (built), the latter
+with searches continuing after intact multi-hop augmentations (built), and on top of that the reduced-cost start with
+its greedy pass (built in round 2).  Every variant must return the same optimum.
 """
 import sys
 
@@ -18,13 +19,22 @@ sys.path.insert(0, ".")
 from consistent__style_transfer_b200 import workload  # noqa: E402
 
 
-def solve(C, sup, dem, cont):
+def solve(C, sup, dem, cont, reduced_start=False):
     """Successive shortest paths, row by row, Dijkstra over the columns; a direct arc out of the root never ends a
-    search; with cont a multi-hop augmentation that empties no reverse arc does not either."""
+    search; with cont a multi-hop augmentation that empties no reverse arc does not either.  reduced_start: duals from a
+    row and a column reduction, then one greedy pass shipping every row along a tight arc into a column with a deficit
+    (what transport_solve_small does before its first search)."""
     m, n = C.shape
     u = np.zeros(m, np.int64); v = np.zeros(n, np.int64)
     F = np.zeros((m, n), np.int64); dem = dem.copy(); sup = sup.copy()
     nsearch = nsel = nrelax = naug = 0
+    if reduced_start:
+        u = C.min(1).astype(np.int64)
+        v = (C - u[:, None]).min(0).astype(np.int64)
+        for r in range(m):
+            tight = np.nonzero((C[r] - u[r] - v == 0) & (dem > 0))[0]
+            if len(tight) and sup[r] > 0:
+                j = int(tight[0]); amt = min(sup[r], dem[j]); F[r, j] += amt; sup[r] -= amt; dem[j] -= amt
     for r in range(m):
         while sup[r] > 0:
             nsearch += 1
@@ -106,9 +116,10 @@ def main():
         C, s, t = pr; n += 1
         big = (C, s, t) if C.shape[0] >= C.shape[1] else (C.T.copy(), t.copy(), s.copy())
         ref = None
-        for name, (prob, cont) in {"rows = supplying side": ((C, s, t), False), "rows = larger side": (big, False),
-                                   "rows = larger side, searches continue": (big, True)}.items():
-            val, cnt = solve(*prob, cont)
+        for name, (prob, cont, red) in {"rows = supplying side": ((C, s, t), False, False), "rows = larger side": (big, False, False),
+                                        "rows = larger side, searches continue": (big, True, False),
+                                        "... and a reduced-cost start with a greedy pass": (big, True, True)}.items():
+            val, cnt = solve(*prob, cont, red)
             ref = val if ref is None else ref
             assert val == ref, (name, val, ref)
             tot[name] = tot.get(name, 0) + cnt
