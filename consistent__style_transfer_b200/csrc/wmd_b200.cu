@@ -127,6 +127,7 @@ struct wmd_engine {
     void *pin_in = nullptr, *pin_out = nullptr;  // wmd_pairs_submit / wmd_pairs_wait: handle-owned pinned staging
     size_t pin_in_cap = 0, pin_out_cap = 0;
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
+    int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
     bool b_global = true;                        // class B costs in L2-resident global scratch (24 instead of 12 warps per SM: 64-token pairs 28 -> 19 ms per 2^18); WMD_B_GLOBAL=0: shared memory
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
@@ -675,12 +676,16 @@ int enqueue_host_job(wmd_engine *E, const HostJob &J)
     // The offsets are validated and measured chunk by chunk, while the GPU works on the chunks already
     // queued: one pass over all of them up front cost 1.5 ms of a 16 ms call (16 MB the caller just wrote).
     int slot = 0;
-    int64_t Bnext = 0;
+    int64_t Bnext = 0, nchunk = 0;
+    const bool fused = takes_fused(E, J.solve, J.rwmd, J.mode);
     for (int64_t c0 = 0; c0 < J.npairs; c0 += Bnext, slot = (slot ^ 1) & E->slot_mask) {
-        const int64_t Btry = std::min<int64_t>(65536, J.npairs - c0);
+        // table mode: the first chunks are small so that the first kernel starts early, later ones larger (fewer kernel tails)
+        const int64_t want = fused ? std::min<int64_t>(E->host_chunk_max, (int64_t)E->host_chunk_first << std::min<int64_t>(nchunk, 8)) : 65536;
+        ++nchunk;
+        const int64_t Btry = std::min<int64_t>(want, J.npairs - c0);
         int32_t ml1, ml2;
         if ((rc = scan_offsets(J.off1 + c0, Btry, ml1, "side 1")) || (rc = scan_offsets(J.off2 + c0, Btry, ml2, "side 2"))) return rc;
-        const int32_t Bc = (int32_t)std::min<int64_t>(Btry, chunk_pairs(ml1, ml2, takes_fused(E, J.solve, J.rwmd, J.mode)));   // a shorter prefix keeps the same bounds
+        const int32_t Bc = fused ? (int32_t)Btry : (int32_t)std::min<int64_t>(Btry, chunk_pairs(ml1, ml2, false));   // a shorter prefix keeps the same bounds
         Bnext = Bc;
         Workspace &W = E->ws[slot];
         cudaStream_t st = E->streams[slot];
@@ -1185,6 +1190,10 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
         if ((rc = setup_fast_path(E))) return bail(rc);
         if (const char *v = getenv("WMD_SERIAL")) E->slot_mask = atoi(v) ? 0 : 1;
         if (const char *v = getenv("WMD_SOLVE_BLOCKS")) E->solve_blocks_per_sm = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_HOST_CHUNK")) {
+            int a = 0, b = 0;
+            if (sscanf(v, "%d,%d", &a, &b) == 2 && a >= 1024 && b >= a) { E->host_chunk_first = a; E->host_chunk_max = std::min(b, 1 << 20); }
+        }
         if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
         if (const char *v = getenv("WMD_B_GLOBAL")) E->b_global = atoi(v) != 0;
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
