@@ -1389,7 +1389,7 @@ int wmd_workspace_bytes(wmd_handle E, int64_t npairs, int32_t max_len1, int32_t 
     const size_t fixed = (size_t)E->V * E->ld * 4 + (size_t)E->nmap * 4 + (E->rank ? (size_t)E->V * 4 : 0) +
                          (table ? (size_t)E->V * E->V * 4 : 0);
     if (estimate) {
-        const int64_t Bc = std::min<int64_t>(npairs, chunk_pairs(ml1, ml2, table));
+        const int64_t Bc = std::min<int64_t>(npairs, table ? std::max<int64_t>(E->host_chunk_max, 65536) : chunk_pairs(ml1, ml2, false));
         const int slots = npairs > Bc ? 2 : 1;
         size_t per = (size_t)Bc * (2 * 8 + 8 + 4 + 4);                                   // offsets, out, status, biglist
         per += (size_t)Bc * (size_t)(ml1 + ml2) * 4;                                     // staged ids (upper bound)
