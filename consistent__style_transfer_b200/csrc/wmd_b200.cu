@@ -1502,6 +1502,7 @@ int wmd_nbow_host(wmd_handle E, const int32_t *ids, const int64_t *off, int64_t 
     if (ndocs > 0x7fffffff) return fail(WMD_EINVAL, "too many documents");
     int rc;
     if ((rc = set_device(E))) return rc;
+    if (E->pending_pairs >= 0) return fail(WMD_EINVAL, "a submitted job is still in flight: call wmd_pairs_wait first");   // shares the slot-0 workspace
     E->ids_are_rows = false;
     int32_t ml;
     if ((rc = scan_offsets(off, ndocs, ml, "documents"))) return rc;

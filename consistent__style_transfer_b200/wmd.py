@@ -276,6 +276,10 @@ class WMDdistance:
         n = min(len(xs1), len(xs2))                           # zip() semantics
         if n == 0:
             return PendingLabels(None, 0, None, None)
+        prev = getattr(self, "_pending", None)
+        if prev is not None:                                  # a handle the caller never collected: finish it, the engine
+            prev._labels()                                    # holds one job at a time
+            self._pending = None
         eng = self.model.wv.device_engine(tokenizer)          # tokenizer ids -> rows on the device
         ids1, off1 = docs_to_csr(xs1[:n])
         ids2, off2 = docs_to_csr(xs2[:n])
@@ -284,6 +288,7 @@ class WMDdistance:
             pending._dist, _ = eng.wmd_pairs(ids1, off1, ids2, off2)
         else:
             eng.submit_pairs(ids1, off1, ids2, off2)
+            self._pending = pending
         return pending
 
     def cal_wmd_padded(self, a, b, tokenizer, pad_id: int = 0):
