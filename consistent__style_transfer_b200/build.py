@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwmd_b200.so")
 SOURCES = ["wmd_b200.cu"]
-HEADERS = ["common.cuh", "nbow.cuh", "cost.cuh", "cost_fast.cuh", "solve.cuh", "fused.cuh", "rwmd.cuh", "allpairs.cuh", "emd.cuh"]
+HEADERS = ["common.cuh", "nbow.cuh", "cost.cuh", "cost_fast.cuh", "solve.cuh", "solve_wide.cuh", "fused.cuh", "rwmd.cuh", "allpairs.cuh", "emd.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # float32 distances must round every op separately (numpy parity)

@@ -189,9 +189,7 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
         const bool swap = sQ > sP;                                       // heavier side supplies
         const int m = swap ? nQ : nP;
         const int nc = (swap ? nP : nQ) + ((sP != sQ) ? 1 : 0);
-        int cls = kClsA;
-        if (m > 192 || nc > 192) cls = kClsF; else if (m > 128 || nc > 160) cls = kClsE; else if (m > 96 || nc > 96) cls = kClsD;
-        else if (m > 64 || nc > 64) cls = kClsC; else if (m > 32 || nc > 32) cls = kClsB;
+        const int cls = solver_class(m, nc);
         meta = cls | (swap ? kMetaSwap : 0);
         if (lane == 0) {
             w.u12[q] = u1 | (u2 << 16);

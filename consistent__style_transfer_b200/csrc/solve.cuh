@@ -28,8 +28,8 @@ struct SolveArgs {
     int32_t cls;                      // class this launch serves (kClsA also finalises kClsNone pairs with status 0)
     int32_t mr, mc;                   // row / column capacity of the per-warp matrices
     int32_t ldc;                      // column pitch (odd)
-    int32_t use_global;               // cost matrix in global scratch as well (class C)
-    int32_t *scratch;                 // classes B / C: [warps, mr * ldc] flow (+ the same again for cost when use_global)
+    int32_t _pad;
+    int32_t *scratch;                 // wide classes: [warps, 2 * mr * ldc] quantised costs + flow
     const int32_t *ip1, *ip2;
     const int32_t *u12, *meta;
     const double *pqn, *extra;
@@ -50,16 +50,32 @@ struct SolveArgs {
     float *maxc_w;
 };
 
+// Reads of the word-distance table are single-use 32-byte sectors scattered over V x V floats: they bypass L1 and
+// are the first lines L2 gives up, so that they do not push the solvers' cost matrices out.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_once(const float *ptr, uint64_t policy)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(policy));
+    return v;
+}
+
 // Largest entry of the u1 x u2 tile of D addressed by the unique rows r1 / r2 (pyemd's maxC is over the FULL matrix).
 __device__ __forceinline__ float gather_tile_max(const float *D, int64_t V, const int32_t *r1, const int32_t *r2, int u1, int u2, int lane)
 {
     unsigned mx = 0;
     const int ncell = u1 * u2;
     const float inv = 1.0f / (float)u2;
+    const uint64_t once = l2_evict_first_policy();
     for (int c = lane; c < ncell; c += kWarp) {
         const int i = (int)(((float)c + 0.5f) * inv);                // c / u2: exact for c < 2^16, u2 <= 256
         const int j = c - i * u2;
-        mx = max(mx, __float_as_uint(__ldg(D + (int64_t)__ldg(r1 + i) * V + __ldg(r2 + j))));
+        mx = max(mx, __float_as_uint(ldg_once(D + (int64_t)__ldg(r1 + i) * V + __ldg(r2 + j), once)));
     }
     return __uint_as_float(__reduce_max_sync(kFull, mx));            // distances are >= 0: uint order == float order
 }
@@ -372,366 +388,6 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
             dist = __ddiv_rn(dist, Cn);
             dist = __dadd_rn(dist, __dmul_rn(A.extra[q], maxc_d));
             A.out[A.p0 + q] = dist;
-        }
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Classes B (<= 64 x 64) and C .. F (<= 96 x 96, 128 x 160, 192 x 192, 256 x 257): the class-A design with KR row words and KC column
-// words.  Lane L is rows L + 32k (k < KR) and columns L + 32k (k < KC); duals, tentative distances and
-// tree predecessors stay in registers, the tree / used-column sets are KR / KC warp-uniform words,
-// and cmask[j][KR] (shared memory) says which rows ship into column j.  The flow matrix is only ever
-// touched along augmenting paths and where cmask has a bit, so it lives in global scratch and is never
-// cleared (a cell is written, not added to, when its bit is off).  Costs: shared memory (class B) or
-// L2-resident global scratch (classes C .. F).  Every selection step walks all KC column words and every new tree row
-// all KR row words, and the register arrays grow with both, so each size class has its own instance -- <3, 3>, <4, 5>,
-// <6, 6>, <8, 9> -- its own launch, register count and scratch pitch: 187 x 188 problems (256-token documents) run 2.2x
-// faster in <6, 6> than they did in <8, 9>, 103 x 104 ones 2.3x faster in <4, 5>.  The previous version kept dense cost AND flow per warp in
-// shared memory (35 kB: 4 warps per SM) and found the rows of a saturated column by scanning a flow
-// column with dependent loads; profiles/README.md has the before / after.
-// ------------------------------------------------------------------------------------------------
-template <int KR, int KC>
-__host__ __device__ inline size_t solve_multi_smem_per_warp(int mr, int mc, int ldc, bool cost_global)
-{
-    size_t ints = (size_t)mr + mc + (size_t)mc * KR;
-    if (!cost_global) ints += (size_t)mr * ldc;
-    return ((ints + 3) & ~(size_t)3) * 4;
-}
-
-template <int K>
-__device__ __forceinline__ int sel_word(const int (&a)[K], int k)
-{
-    int x = a[0];
-#pragma unroll
-    for (int t = 1; t < K; ++t) if (t == k) x = a[t];
-    return x;
-}
-
-template <int KR, int KC>
-__device__ long long transport_solve_multi(int m, int nc, int ldc, const int *cost, int *flow, unsigned *cmask,
-                                           const int (&supply)[KR], int (&deficit)[KC], int lane)
-{
-    int u[KR], rdist[KR], rpred[KR];
-    int v[KC], minv[KC], way[KC];
-    unsigned tree[KR], used[KC], inval[KC];
-#pragma unroll
-    for (int k = 0; k < KR; ++k) u[k] = 0;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        v[k] = 0;
-        const int lo = 32 * k;                                   // columns >= nc do not exist: permanently "used"
-        inval[k] = nc >= lo + 32 ? 0u : (nc <= lo ? kFull : (kFull << (nc - lo)));
-    }
-    for (int x = lane; x < nc * KR; x += kWarp) cmask[x] = 0;
-    __syncwarp();
-    const unsigned lbit = 1u << lane;
-    int srem[KR];                                                // supply still to ship; `supply` stays as handed in
-#pragma unroll
-    for (int k = 0; k < KR; ++k) srem[k] = supply[k];
-    // Reduced-cost start with one greedy pass over tight arcs (see transport_solve_small) -- for problems of up to 64 x 64
-    // only: the python model (tools/solver_model.py) counts 36 % fewer column selections at 64 tokens, no change at 128 and
-    // 50 % MORE at 256, where the greedy shipments along near-tied arcs have to be re-routed one by one.
-    if constexpr (KR <= 2) {
-        for (int r = 0; r < m; ++r) {                            // u_r = the row's cheapest arc
-            int best = kIntInf;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) if (!(inval[k] & lbit)) best = min(best, cost[r * ldc + lane + 32 * k]);
-            best = __reduce_min_sync(kFull, best);
-#pragma unroll
-            for (int k = 0; k < KR; ++k) if (r == lane + 32 * k) u[k] = best;
-        }
-        {                                                        // v_c = what is left of the column's cheapest arc
-            int best[KC];
-#pragma unroll
-            for (int k = 0; k < KC; ++k) best[k] = kIntInf;
-            for (int r = 0; r < m; ++r) {
-                const int ur = __shfl_sync(kFull, sel_word<KR>(u, r >> 5), r & 31);
-#pragma unroll
-                for (int k = 0; k < KC; ++k) if (!(inval[k] & lbit)) best[k] = min(best[k], cost[r * ldc + lane + 32 * k] - ur);
-            }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) if (!(inval[k] & lbit)) v[k] = best[k];
-        }
-        for (int r = 0; r < m; ++r) {                            // every row ships along a tight arc into a column with a deficit
-            const int rk = r >> 5, rl = r & 31;
-            const int ur = __shfl_sync(kFull, sel_word<KR>(u, rk), rl), sr = __shfl_sync(kFull, sel_word<KR>(srem, rk), rl);
-            int jk = -1, jl = 0;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const bool open = !(inval[k] & lbit) && deficit[k] > 0 && cost[r * ldc + lane + 32 * k] - ur - v[k] == 0;
-                const unsigned cand = __ballot_sync(kFull, open);
-                if (jk < 0 && cand) { jk = k; jl = __ffs(cand) - 1; }
-            }
-            if (jk < 0 || sr == 0) continue;
-            const int amt = min(sr, __shfl_sync(kFull, sel_word<KC>(deficit, jk), jl));
-            const int j0 = jl + 32 * jk;
-            if (lane == jl) {
-                flow[r * ldc + j0] = amt;
-                cmask[j0 * KR + rk] |= 1u << rl;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
-            }
-            if (lane == rl) {
-#pragma unroll
-                for (int k = 0; k < KR; ++k) if (k == rk) srem[k] -= amt;
-            }
-        }
-        __syncwarp();
-    }
-
-    for (int r = 0; r < m; ++r) {
-        const int rk = r >> 5, rl = r & 31;
-        int sup = __shfl_sync(kFull, sel_word<KR>(srem, rk), rl);
-        while (sup > 0) {
-#pragma unroll
-            for (int k = 0; k < KR; ++k) { tree[k] = k == rk ? (1u << rl) : 0u; rdist[k] = 0; rpred[k] = -1; }
-            {
-                const int ur = __shfl_sync(kFull, sel_word<KR>(u, rk), rl);
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    used[k] = inval[k];
-                    way[k] = r;
-                    minv[k] = (inval[k] & lbit) ? kIntInf : cost[r * ldc + lane + 32 * k] - ur - v[k];
-                }
-            }
-            int delta, j0, jl, jk, def;
-            for (;;) {
-                int best = kIntInf, bk = 0;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int key = (used[k] & lbit) ? kIntInf : minv[k];
-                    if (key < best) { best = key; bk = k; }
-                }
-                delta = __reduce_min_sync(kFull, best);
-                if (delta >= kIntInf) return -1;                 // unbalanced input: cannot happen, never spin
-                jl = __ffs(__ballot_sync(kFull, best == delta)) - 1;
-                jk = __shfl_sync(kFull, bk, jl);
-                j0 = jl + 32 * jk;
-#pragma unroll
-                for (int k = 0; k < KC; ++k) if (k == jk) used[k] |= 1u << jl;
-                def = __shfl_sync(kFull, sel_word<KC>(deficit, jk), jl);
-                if (def > 0) {
-                    // ship along the tree path and keep searching while the tree stays intact (see transport_solve_small)
-                    int amt;
-                    bool intact = true;
-                    if (__shfl_sync(kFull, sel_word<KC>(way, jk), jl) == r) {
-                        amt = min(sup, def);
-                        if (lane == jl) {
-                            const unsigned w = cmask[j0 * KR + rk];
-                            int *f = flow + r * ldc + j0;
-                            *f = (w >> rl) & 1u ? *f + amt : amt;
-                            cmask[j0 * KR + rk] = w | (1u << rl);
-                        }
-                    } else {
-                        // tree path j0 -> ... -> r in pieces of 32 hops (hop h = row pi starts shipping into column pj
-                        // and stops shipping amt into its tree predecessor column pjp); pass 0 finds the bottleneck, the
-                        // push follows at once when the path fits one piece, otherwise pass 1 walks it again
-                        int bott = kIntInf;
-                        amt = min(sup, def);
-                        for (int pass = 0; pass < 2; ++pass) {
-                            int j = j0;
-                            bool done = false, single = true;
-                            while (!done) {
-                                int pi = 0, pj = 0, pjp = -1, nh = 0;
-                                for (; nh < kWarp;) {
-                                    const int i = __shfl_sync(kFull, sel_word<KC>(way, j >> 5), j & 31);
-                                    const int jp = __shfl_sync(kFull, sel_word<KR>(rpred, i >> 5), i & 31);
-                                    if (lane == nh) { pi = i; pj = j; pjp = i == r ? -1 : jp; }
-                                    ++nh;
-                                    if (i == r) { done = true; break; }
-                                    j = jp;
-                                }
-                                if (!done) single = false;
-                                const bool hop = lane < nh;
-                                const int frev = (hop && pjp >= 0) ? flow[pi * ldc + pjp] : kIntInf;
-                                if (pass == 0) { bott = min(bott, __reduce_min_sync(kFull, frev)); amt = min(amt, bott); }
-                                if ((pass == 0 && single && done) || pass == 1) {
-                                    if (hop) {
-                                        const unsigned bit = 1u << (pi & 31);
-                                        const unsigned old = atomicOr(&cmask[pj * KR + (pi >> 5)], bit);
-                                        int *f = flow + pi * ldc + pj;
-                                        *f = (old & bit) ? *f + amt : amt;
-                                        if (pjp >= 0) {
-                                            flow[pi * ldc + pjp] = frev - amt;
-                                            if (frev == amt) atomicAnd(&cmask[pjp * KR + (pi >> 5)], ~bit);
-                                        }
-                                    }
-                                    __syncwarp();
-                                }
-                            }
-                            if (single) break;
-                        }
-                        intact = amt < bott;                     // no reverse arc of the path ran empty
-                    }
-                    if (lane == jl) {
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) if (k == jk) deficit[k] -= amt;
-                    }
-                    __syncwarp();
-                    sup -= amt;
-                    def -= amt;
-                    if (sup == 0 || !intact) break;              // the row is empty, or the search has to start again
-                }
-                // rows shipping into the saturated column join the tree at distance delta
-#pragma unroll
-                for (int w = 0; w < KR; ++w) {
-                    unsigned nr = cmask[j0 * KR + w] & ~tree[w];
-                    tree[w] |= nr;
-                    if (nr & lbit) { rdist[w] = delta; rpred[w] = j0; }
-                    while (nr) {
-                        const int b = __ffs(nr) - 1;
-                        nr &= nr - 1;
-                        const int i = 32 * w + b;
-                        const int base = delta - __shfl_sync(kFull, u[w], b);
-                        const int *crow = cost + i * ldc + lane;
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            if (!(used[k] & lbit)) {
-                                const int cand = base + crow[32 * k] - v[k];
-                                if (cand < minv[k]) { minv[k] = cand; way[k] = i; }
-                            }
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < KR; ++k) if (tree[k] & lbit) u[k] += delta - rdist[k];     // dual update (tree nodes only)
-#pragma unroll
-            for (int k = 0; k < KC; ++k) if (used[k] & ~inval[k] & lbit) v[k] -= delta - minv[k];
-        }
-    }
-    long long tot = 0;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int c = lane + 32 * k;
-        if (c < nc) {
-#pragma unroll
-            for (int w = 0; w < KR; ++w) {
-                unsigned bits = cmask[c * KR + w];
-                while (bits) {
-                    const int i = 32 * w + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    tot += (long long)flow[i * ldc + c] * (long long)cost[i * ldc + c];
-                }
-            }
-        }
-    }
-    return warp_sum_ll(tot);
-}
-
-template <int KR, int KC, bool GC, bool GATHER>
-__global__ void __launch_bounds__(KR > 2 ? 128 : 256)
-emd_solve_multi_kernel(const __grid_constant__ SolveArgs A)
-{
-    extern __shared__ __align__(16) int smem_i[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int ldc = A.ldc;
-    int *sb = smem_i + (size_t)wib * (solve_multi_smem_per_warp<KR, KC>(A.mr, A.mc, ldc, GC) / 4);
-    int *sridx = sb, *scidx = sb + A.mr;
-    unsigned *cmask = reinterpret_cast<unsigned *>(scidx + A.mc);
-    int *cost, *flow;
-    {
-        const size_t w = (size_t)blockIdx.x * wpb + wib, mat = (size_t)A.mr * ldc;
-        if (GC) { cost = A.scratch + w * 2 * mat; flow = cost + mat; }
-        else    { cost = reinterpret_cast<int *>(cmask + (size_t)A.mc * KR); flow = A.scratch + w * mat; }
-    }
-    int64_t tok1, tok2;
-    { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }
-    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-    const int npairs = A.nlist ? (int)*A.nlist : A.npairs;
-
-    for (;;) {
-        int q = 0;
-        if (lane == 0) q = (int)atomicAdd(A.counter, 1u);
-        q = __shfl_sync(kFull, q, 0);
-        if (q >= npairs) break;
-        if (A.list) q = A.list[q];
-        const int meta = A.meta[q];
-        if ((meta & 7) != A.cls) continue;
-        const int64_t p = A.p0 + q;
-        const int uu = A.u12[q];
-        const int u1 = uu & 0xffff, u2 = uu >> 16;
-        const bool swap = (meta & kMetaSwap) != 0;
-        int64_t a1, a2; int l;
-        doc_span(A.s1, p, a1, l); doc_span(A.s2, p, a2, l);
-        const int32_t *r1 = nullptr, *r2 = nullptr;
-        if (GATHER) { r1 = A.rows1 + slot_off(A.s1, tok1, q, a1); r2 = A.rows2 + slot_off(A.s2, tok2, q, a2); }
-        const float maxc_f = GATHER ? gather_tile_max(A.D, A.V, r1, r2, u1, u2, lane) : A.maxc[q];
-        if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
-            continue;
-        }
-        const int32_t *ipR = swap ? A.ip2 + slot_off(A.s2, tok2, q, a2) : A.ip1 + slot_off(A.s1, tok1, q, a1);   // supplying side
-        const int32_t *ipC = swap ? A.ip1 + slot_off(A.s1, tok1, q, a1) : A.ip2 + slot_off(A.s2, tok2, q, a2);
-        const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
-        int m = 0, n = 0, sumR = 0, sumC = 0;
-        for (int base = 0; base < uR; base += kWarp) {           // compact the residual rows: (mass << 8) | index
-            const int i = base + lane;
-            const int x = i < uR ? ipR[i] : 0;
-            const unsigned bal = __ballot_sync(kFull, x > 0);
-            if (x > 0) sridx[m + __popc(bal & ((1u << lane) - 1))] = (x << 8) | i;
-            m += __popc(bal);
-            sumR += x;
-        }
-        for (int base = 0; base < uC; base += kWarp) {
-            const int j = base + lane;
-            const int x = j < uC ? ipC[j] : 0;
-            const unsigned bal = __ballot_sync(kFull, x > 0);
-            if (x > 0) scidx[n + __popc(bal & ((1u << lane) - 1))] = (x << 8) | j;
-            n += __popc(bal);
-            sumC += x;
-        }
-        sumR = warp_sum(sumR); sumC = warp_sum(sumC);
-        __syncwarp();
-        const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
-        long long opt = 0;
-        if (n > 0 && m > 0) {
-            const int diff = sumR - sumC;                        // >= 0 by the choice of the supplying side
-            const int nc = n + (diff > 0 ? 1 : 0);
-            int supply[KR], deficit[KC], cj[KC];
-#pragma unroll
-            for (int k = 0; k < KR; ++k) { const int i = lane + 32 * k; supply[k] = i < m ? sridx[i] >> 8 : 0; }
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int c = lane + 32 * k;
-                const int pc = c < n ? scidx[c] : 0;
-                cj[k] = pc & 0xff;
-                deficit[k] = c < n ? pc >> 8 : (c == n ? diff : 0);
-            }
-            // quantised costs of the residual sub-tile (S6(d)); the dummy column costs 0
-            const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
-            if (GATHER) {                                        // cj[k] becomes the table row of column k's token
-#pragma unroll
-                for (int k = 0; k < KC; ++k) cj[k] = lane + 32 * k < n ? __ldg((swap ? r1 : r2) + cj[k]) : 0;
-            }
-            for (int rI = 0; rI < m; ++rI) {
-                const int i = sridx[rI] & 0xff;
-                const float *drow = GATHER ? A.D + (int64_t)__ldg((swap ? r2 : r1) + i) * A.V : nullptr;      // D is symmetric
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int c = lane + 32 * k;
-                    if (c < nc) {
-                        int ic = 0;
-                        if (c < n) {
-                            float dv;
-                            if (GATHER) dv = __ldg(drow + cj[k]);
-                            else dv = swap ? tile[(int64_t)cj[k] * u2 + i] : tile[(int64_t)i * u2 + cj[k]];
-                            ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
-                        }
-                        cost[rI * ldc + c] = ic;
-                    }
-                }
-            }
-            __syncwarp();
-            opt = transport_solve_multi<KR, KC>(m, nc, ldc, cost, flow, cmask, supply, deficit, lane);
-        }
-        if (lane == 0) {
-            double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;
-            dist = __ddiv_rn(dist, A.pqn[q]);                     // S6(f)
-            dist = __ddiv_rn(dist, Cn);
-            dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
-            A.out[p] = dist;
         }
         __syncwarp();
     }

@@ -3,7 +3,7 @@
 // Pipeline per chunk of pairs (all on one CUDA stream, chunks alternate between two streams so
 // that the FP32-bound cost kernel of one chunk overlaps the latency-bound solver of the other
 // and the chunk's tiles stay L2-resident between the two):
-//     K1 nbow_pairs_kernel -> K2 cost_plan_kernel + cost_tiles_fast_kernel -> K3 emd_solve_small_kernel / emd_solve_multi_kernel
+//     K1 nbow_pairs_kernel -> K2 cost_plan_kernel + cost_tiles_fast_kernel -> K3 emd_solve_small_kernel / emd_solve_wide_kernel
 // There is no CPU implementation behind this ABI: without a device every entry fails.
 #include "../../include/wmd_b200.h"
 
@@ -22,6 +22,7 @@
 #include "cost.cuh"
 #include "cost_fast.cuh"
 #include "solve.cuh"
+#include "solve_wide.cuh"
 #include "fused.cuh"
 #include "rwmd.cuh"
 #include "allpairs.cuh"
@@ -129,7 +130,6 @@ struct wmd_engine {
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
     int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
-    bool b_global = true;                        // class B costs in L2-resident global scratch (24 instead of 12 warps per SM: 64-token pairs 28 -> 19 ms per 2^18); WMD_B_GLOBAL=0: shared memory
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
@@ -375,26 +375,23 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
 
 // K3 launches of one chunk: one launch per solver class over all pairs of the chunk, or (list mode) over the pairs the
 // fused kernel left behind.  gather: costs come from the word-distance table instead of cost tiles.
-struct SolverClass { int cls, rows, cols, min_ml; };            // capacity of the class and the shortest longer side that can produce it
-constexpr SolverClass kSolverClasses[] = {
-    { kClsA, 32, 32, 1 },  { kClsB, 64, 64, 32 },  { kClsC, 96, 96, 64 },  { kClsD, 128, 160, 96 },
-    { kClsE, 192, 192, 129 },  { kClsF, kMaxDocLen, kMaxDocLen + 1, 192 },
+struct WideClass { int cls, kc, min_ml; };                      // instance (column words of the shorter side) and the shortest longest
+constexpr WideClass kWideClasses[] = {                          // document of a chunk that can produce a problem of the class
+    { kClsW1, 1, 32 }, { kClsW2, 2, 33 }, { kClsW3, 3, 65 }, { kClsW4, 4, 97 }, { kClsW6, 6, 129 }, { kClsW8, 8, 193 },
 };
 
 template <class K>
-int launch_multi_solver(wmd_engine *E, Workspace &W, cudaStream_t st, K kernel, SolveArgs &S, size_t per_warp, int32_t Bc)
+int launch_wide_solver(wmd_engine *E, Workspace &W, cudaStream_t st, K kernel, SolveArgs &S, size_t per_warp, int32_t Bc)
 {
     int rc;
-    int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    const int wpb = 4;
     const size_t smem = per_warp * wpb;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, wpb * 32, smem));
     if (nb < 1) return fail(WMD_ECUDA, "solver class %d cannot be resident", S.cls);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + wpb - 1) / wpb, (int64_t)E->sm_count * nb));
-    // per warp: flow (class B; its costs sit in shared memory), cost + flow (larger classes)
-    if ((rc = W.scratch.ensure((size_t)grid * wpb * (S.use_global ? 2 : 1) * S.mr * S.ldc * 4))) return rc;
+    if ((rc = W.scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;      // per warp: quantised costs + flow
     S.scratch = W.scratch.as<int32_t>();
     Prof pr(E, WMD_K_SOLVE, st);
     kernel<<<grid, wpb * 32, smem, st>>>(S);
@@ -407,50 +404,53 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
                    const unsigned int *nlist, bool gather)
 {
     int rc;
-    for (const SolverClass &C : kSolverClasses) {
-        if (ML < C.min_ml) continue;                  // no document of the chunk is long enough for a residual problem of this class
-        const int cls = C.cls;
-        SolveArgs S;
-        S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc; S.cls = cls;
-        S.mr = std::min(C.rows, ML); S.mc = std::min(C.cols, ML + 1);
-        if (cls == kClsA) S.mr = S.mc;                // class A may turn the problem round: the dummy then is a row
+    SolveArgs S;
+    S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc;
+    S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
+    S.tiles = tiles; S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
+    S.out = O.out; S.status = O.status;
+    S.list = list; S.nlist = nlist;
+    S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
+    S.scratch = nullptr;
+    {                                                 // class A: both sides of the residual problem fit one word
+        S.cls = kClsA;
+        S.mr = S.mc = std::min(32, ML + 1);           // class A may turn the problem round: the dummy then is a row
         S.ldc = S.mc | 1;
-        S.use_global = cls >= kClsC;
-        S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
-        S.tiles = tiles; S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
-        S.counter = W.counters.as<unsigned int>() + cls;
-        S.out = O.out; S.status = O.status;
-        S.list = list; S.nlist = nlist;
-        S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
-        S.scratch = nullptr;
-        if (cls == kClsA) {
-            const int wpb = 4;
-            const size_t smem = solve_small_smem_per_warp(S.mr, S.mc, S.ldc) * wpb;
-            const int blocks_per_sm = E->solve_blocks_per_sm * 2;                         // __launch_bounds__(128, 9)
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * blocks_per_sm));
-            Prof pr(E, WMD_K_SOLVE, st);
-            if (gather) {
-                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                emd_solve_small_kernel<true><<<grid, wpb * 32, smem, st>>>(S);
-            } else {
-                if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                emd_solve_small_kernel<false><<<grid, wpb * 32, smem, st>>>(S);
-            }
-            CK(cudaGetLastError());
-            continue;
+        S.counter = W.counters.as<unsigned int>() + kClsA;
+        const int wpb = 4;
+        const size_t smem = solve_small_smem_per_warp(S.mr, S.mc, S.ldc) * wpb;
+        const int blocks_per_sm = E->solve_blocks_per_sm * 2;                         // __launch_bounds__(128, 9)
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * blocks_per_sm));
+        Prof pr(E, WMD_K_SOLVE, st);
+        if (gather) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_small_kernel<true><<<grid, wpb * 32, smem, st>>>(S);
+        } else {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emd_solve_small_kernel<false><<<grid, wpb * 32, smem, st>>>(S);
         }
-#define WMD_MULTI(KR, KC, GC)                                                                                                        \
-        (gather ? launch_multi_solver(E, W, st, emd_solve_multi_kernel<KR, KC, GC, true>, S, solve_multi_smem_per_warp<KR, KC>(S.mr, S.mc, S.ldc, GC), Bc) \
-                : launch_multi_solver(E, W, st, emd_solve_multi_kernel<KR, KC, GC, false>, S, solve_multi_smem_per_warp<KR, KC>(S.mr, S.mc, S.ldc, GC), Bc))
-        if (cls == kClsB) {
-            if (E->b_global) { S.use_global = 1; rc = WMD_MULTI(2, 2, true); }
-            else rc = WMD_MULTI(2, 2, false);
+        CK(cudaGetLastError());
+    }
+    // Larger problems, largest class first.  The per-launch capacity follows the chunk's longest document (rows: one more
+    // for the dummy row); the instance only depends on the pair's own shorter side.
+    for (int ci = (int)(sizeof kWideClasses / sizeof kWideClasses[0]) - 1; ci >= 0; --ci) {
+        const WideClass &C = kWideClasses[ci];
+        if (ML < C.min_ml) continue;                  // no document of the chunk is long enough for a problem of this class
+        S.cls = C.cls;
+        S.mr = std::min(C.cls == kClsW8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1); S.mc = 32 * C.kc; S.ldc = 32 * C.kc;
+        S.counter = W.counters.as<unsigned int>() + C.cls;
+#define WMD_WIDE(KC, MINB)                                                                                                           \
+        (gather ? launch_wide_solver(E, W, st, emd_solve_wide_kernel<KC, true, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc)      \
+                : launch_wide_solver(E, W, st, emd_solve_wide_kernel<KC, false, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc))
+        switch (C.kc) {
+        case 1: rc = WMD_WIDE(1, 8); break;
+        case 2: rc = WMD_WIDE(2, 8); break;
+        case 3: rc = WMD_WIDE(3, 6); break;
+        case 4: rc = WMD_WIDE(4, 6); break;
+        case 6: rc = WMD_WIDE(6, 5); break;
+        default: rc = WMD_WIDE(8, 4); break;
         }
-        else if (cls == kClsC) rc = WMD_MULTI(3, 3, true);
-        else if (cls == kClsD) rc = WMD_MULTI(4, 5, true);
-        else if (cls == kClsE) rc = WMD_MULTI(6, 6, true);
-        else rc = WMD_MULTI(8, 9, true);
-#undef WMD_MULTI
+#undef WMD_WIDE
         if (rc) return rc;
     }
     return WMD_OK;
@@ -1195,7 +1195,6 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
             if (sscanf(v, "%d,%d", &a, &b) == 2 && a >= 1024 && b >= a) { E->host_chunk_first = a; E->host_chunk_max = std::min(b, 1 << 20); }
         }
         if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
-        if (const char *v = getenv("WMD_B_GLOBAL")) E->b_global = atoi(v) != 0;
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
@@ -1400,8 +1399,10 @@ int wmd_workspace_bytes(wmd_handle E, int64_t npairs, int32_t max_len1, int32_t 
                 per += (size_t)Bc * ml1 * ml2 * 4;                                       // cost tiles
                 per += (size_t)plan_stage_bound(Bc, ml1, ml2, Bc * (int64_t)ml1, Bc * (int64_t)ml2, std::max(E->fast_R, 8), kStageTilesMax) * sizeof(StageRec);
             }
-            if (ML >= 64) per += (size_t)E->sm_count * 12 * 2 * (size_t)std::min(ML, kMaxDocLen) * (std::min(ML, kMaxDocLen) + 2) * 4;   // class C scratch
-            else if (ML >= 32) per += (size_t)E->sm_count * 32 * (size_t)64 * 65 * 4;    // class B flow scratch
+            if (ML >= 32) {                                                              // wide solver scratch: costs + flow per resident warp
+                const int kc = std::min((ML + 31) / 32, 8);                              // (upper bound: 32 warps per SM up to <2>, 24 / 20 / 16 above)
+                per += (size_t)E->sm_count * (kc <= 2 ? 32 : kc <= 4 ? 24 : kc <= 6 ? 20 : 16) * 2 * (size_t)(std::min(ML, kMaxDocLen) + 1) * (32 * (kc == 5 ? 6 : kc == 7 ? 8 : kc)) * 4;
+            }
         }
         *estimate = (int64_t)(fixed + (size_t)slots * per);
     }
