@@ -11,27 +11,24 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxDocLen = 256;          // WMD_MAX_DOC_LEN
 constexpr int kIntInf = 0x3fffffff;      // "infinite" tentative distance (sums of two stay < 2^31)
 
-// per-pair solver classes written by the nBOW kernel (meta & 7)
+// per-pair solver classes written by the nBOW kernel (meta & kMetaCls)
 constexpr int kClsNone = 0;              // nothing to do (early-out already written)
 constexpr int kClsA = 1;                 // residual rows <= 32 and columns (incl. dummy) <= 32: the fused / class-A kernels
-// Larger problems (solve_wide.cuh): rows = the side with more nodes (<= 257 incl. a dummy row), class = the number of
-// 32-column words of the SHORTER side.
-constexpr int kClsW1 = 2;                // shorter side <= 32 columns  (emd_solve_wide_kernel<1>)
-constexpr int kClsW2 = 3;                // <= 64   (<2>)
-constexpr int kClsW3 = 4;                // <= 96   (<3>)
-constexpr int kClsW4 = 5;                // <= 128  (<4>)
-constexpr int kClsW6 = 6;                // <= 192  (<6>)
-constexpr int kClsW8 = 7;                // <= 256  (<8>)
+// Larger problems (solve_wide.cuh): rows = the side with more nodes (<= 257 incl. a dummy row), class = 1 + the number
+// KC of 32-column words of the SHORTER side (emd_solve_wide_kernel<KC>, KC = 1 .. 8).
+constexpr int kClsW1 = 2;
+constexpr int kClsW8 = kClsW1 + 7;
 constexpr int kClsLast = kClsW8;
+constexpr int kMetaCls = 15;
 // class of a residual problem of m supplying rows and nc columns (incl. the dummy column)
 __host__ __device__ inline int solver_class(int m, int nc)
 {
     const int hi = m > nc ? m : nc, lo = m > nc ? nc : m;
     if (hi <= 32) return kClsA;
     if (hi > kMaxDocLen) return kClsW8;                          // 256 nodes a side plus the dummy: the one launch with 257 rows
-    return lo <= 32 ? kClsW1 : lo <= 64 ? kClsW2 : lo <= 96 ? kClsW3 : lo <= 128 ? kClsW4 : lo <= 192 ? kClsW6 : kClsW8;
+    return kClsW1 + ((lo + 31) >> 5) - 1;
 }
-constexpr int kMetaSwap = 8;             // doc2 is the heavier (supplying) side
+constexpr int kMetaSwap = 16;            // doc2 is the heavier (supplying) side
 
 // One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).
 // With sel != nullptr pair p uses document sel[p] (all-pairs candidate lists: many pairs share a

@@ -306,7 +306,7 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
         if (q >= npairs) break;
         if (A.list) q = A.list[q];
         const int meta = A.meta[q];
-        if ((meta & 7) != A.cls) continue;
+        if ((meta & kMetaCls) != A.cls) continue;
         const int64_t p = A.p0 + q;
         const int uu = A.u12[q];
         const int u1 = uu & 0xffff, u2 = uu >> 16;
@@ -316,36 +316,42 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
         const int64_t o1 = slot_off(A.s1, tok1, q, a1), o2 = slot_off(A.s2, tok2, q, a2);
         const int32_t *r1 = nullptr, *r2 = nullptr;
         if (GATHER) { r1 = A.rows1 + o1; r2 = A.rows2 + o2; }
-        const float maxc_f = GATHER ? gather_tile_max(A.D, A.V, r1, r2, u1, u2, lane) : A.maxc[q];
-        if (!(maxc_f > 0.f)) {                                       // S4: all-zero distance matrix
+        float maxc_f = GATHER ? 0.f : A.maxc[q];
+        if (!GATHER && !(maxc_f > 0.f)) {                            // S4: all-zero distance matrix
             if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
             continue;
         }
         const int32_t *ipR = swap ? A.ip2 + o2 : A.ip1 + o1;         // supplying side
         const int32_t *ipC = swap ? A.ip1 + o1 : A.ip2 + o2;
         const int uR = swap ? u2 : u1, uC = swap ? u1 : u2;
-        int m = 0, n = 0, sumR = 0, sumC = 0;
-        for (int base = 0; base < uR; base += kWarp) {               // compact the residual nodes: (mass << 8) | index
+        // Compact the residual nodes to the front of the lists as (mass << 8) | index; nodes without residual mass (the
+        // metric cancellation emptied them) go to the back, index only: pyemd's maxC is over the FULL tile.
+        int m = 0, n = 0, zR = 0, zC = 0, sumR = 0, sumC = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int base = 0; base < uR; base += kWarp) {
             const int i = base + lane;
             const int x = i < uR ? ipR[i] : 0;
-            const unsigned bal = __ballot_sync(kFull, x > 0);
-            if (x > 0) listR[m + __popc(bal & ((1u << lane) - 1))] = (x << 8) | i;
-            m += __popc(bal);
+            const unsigned bal = __ballot_sync(kFull, x > 0), zal = __ballot_sync(kFull, i < uR && x <= 0);
+            if (x > 0) listR[m + __popc(bal & lt)] = (x << 8) | i;
+            else if (i < uR) listR[mrp - 1 - (zR + __popc(zal & lt))] = i;
+            m += __popc(bal); zR += __popc(zal);
             sumR += x;
         }
         for (int base = 0; base < uC; base += kWarp) {
             const int j = base + lane;
             const int x = j < uC ? ipC[j] : 0;
-            const unsigned bal = __ballot_sync(kFull, x > 0);
-            if (x > 0) listC[n + __popc(bal & ((1u << lane) - 1))] = (x << 8) | j;
-            n += __popc(bal);
+            const unsigned bal = __ballot_sync(kFull, x > 0), zal = __ballot_sync(kFull, j < uC && x <= 0);
+            if (x > 0) listC[n + __popc(bal & lt)] = (x << 8) | j;
+            else if (j < uC) listC[mrp - 1 - (zC + __popc(zal & lt))] = j;
+            n += __popc(bal); zC += __popc(zal);
             sumC += x;
         }
         sumR = warp_sum(sumR); sumC = warp_sum(sumC);
         __syncwarp();
-        const double Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+        double Cn = 0.0;
         long long opt = 0;
-        if (n > 0 && m > 0) {
+        bool zero_matrix = false;
+        {
             const int diff = sumR - sumC;                            // >= 0 by the choice of the supplying side
             const int nc = n + (diff > 0 ? 1 : 0);
             // rows = the side with more nodes; flip: the lighter side plus the surplus as a zero-cost dummy ROW are the
@@ -353,6 +359,7 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
             const bool flip = m < nc;
             const int mm = flip ? nc : m, ncc = flip ? m : nc;
             const int nrow = flip ? n : m, ncol = flip ? m : n;      // real (non-dummy) rows / columns
+            const int zrow = flip ? zC : zR, zcol = flip ? zR : zC;  // nodes without residual mass on either side
             const int *rowL = flip ? listC : listR, *colL = flip ? listR : listC;
             const bool rows_doc1 = swap == flip;                     // the rows are doc1's tokens
             int cj[KC];
@@ -364,30 +371,73 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
                 if (GATHER) cj[k] = c < ncol ? __ldg((rows_doc1 ? r2 : r1) + cj[k]) : 0;      // table row of the column's token
                 deficit[c] = c < ncol ? pc >> 8 : ((!flip && c == ncol) ? diff : 0);
             }
-            // quantised costs of the residual sub-tile (S6(d)); the dummy row / column costs 0
-            const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
-            const uint64_t once = l2_evict_first_policy();
-            for (int rI = 0; rI < mm; ++rI) {
-                const int pr = rI < nrow ? rowL[rI] : 0;
-                const int i = pr & 0xff;
-                const float *drow = GATHER ? A.D + (int64_t)__ldg((rows_doc1 ? r1 : r2) + i) * A.V : nullptr;      // D is symmetric
+            if (GATHER) {
+                // One pass over the table: every cell of the full tile is fetched once -- the residual sub-tile lands in
+                // the cost matrix as float bits and is quantised in place once maxC is known.
+                const uint64_t once = l2_evict_first_policy();
+                const int32_t *rtab = rows_doc1 ? r1 : r2, *ctab = rows_doc1 ? r2 : r1;
+                unsigned mx = 0;
+                const int T = nrow + zrow;
+                int *rowtab = srem;                                  // table row of every token of the row document (srem is still free)
+                for (int t = lane; t < T; t += kWarp) rowtab[t] = __ldg(rtab + (t < nrow ? rowL[t] & 0xff : rowL[mrp - 1 - (t - nrow)]));
+                __syncwarp();
+                constexpr int RB = KC <= 2 ? 4 : 2;                  // rows in flight: RB * KC independent gathers per lane
+                for (int t0 = 0; t0 < T; t0 += RB) {                 // all tokens of the row document x residual columns
+                    unsigned bits[RB][KC];
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int c = lane + 32 * k;
-                    int ic = 0;
-                    if (c < ncol && rI < nrow) {
-                        float dv;
-                        if (GATHER) dv = ldg_once(drow + cj[k], once);
-                        else dv = rows_doc1 ? tile[(int64_t)i * u2 + cj[k]] : tile[(int64_t)cj[k] * u2 + i];
-                        ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                    for (int b = 0; b < RB; ++b) {
+                        const float *drow = A.D + (int64_t)rowtab[min(t0 + b, T - 1)] * A.V;     // D is symmetric
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) bits[b][k] = lane + 32 * k < ncol ? __float_as_uint(ldg_once(drow + cj[k], once)) : 0u;
                     }
-                    if (c < ncc) cost[rI * ldc + c] = ic;
+#pragma unroll
+                    for (int b = 0; b < RB; ++b) {
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            mx = max(mx, bits[b][k]);                // distances are >= 0: uint order == float order
+                            if (t0 + b < nrow && lane + 32 * k < ncol) cost[(t0 + b) * ldc + lane + 32 * k] = (int)bits[b][k];
+                        }
+                    }
                 }
+                for (int x = lane; x < T * zcol; x += kWarp) {                      // ... x columns without residual mass
+                    const int t = x / zcol, z = x - t * zcol;
+                    const int j = colL[mrp - 1 - z];
+                    mx = max(mx, __float_as_uint(ldg_once(A.D + (int64_t)rowtab[t] * A.V + __ldg(ctab + j), once)));
+                }
+                mx = __reduce_max_sync(kFull, mx);
+                maxc_f = __uint_as_float(mx);
+                zero_matrix = mx == 0;
             }
-            // supplies last: srem does not alias the lists, u and cmask (which do) are cleared by the solver
-            for (int i = lane; i < mm; i += kWarp) srem[i] = i < nrow ? rowL[i] >> 8 : diff;
+            if (!zero_matrix) Cn = __ddiv_rn(1000000.0, (double)maxc_f);
+            if (!zero_matrix && n > 0 && m > 0) {
+                // quantised costs of the residual sub-tile (S6(d)); the dummy row / column costs 0
+                const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
+                __syncwarp();
+                for (int rI = 0; rI < mm; ++rI) {
+                    const int i = rI < nrow ? rowL[rI] & 0xff : 0;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        const int c = lane + 32 * k;
+                        int ic = 0;
+                        if (c < ncol && rI < nrow) {
+                            float dv;
+                            if (GATHER) dv = __int_as_float(cost[rI * ldc + c]);
+                            else dv = rows_doc1 ? tile[(int64_t)i * u2 + cj[k]] : tile[(int64_t)cj[k] * u2 + i];
+                            ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                        }
+                        if (c < ncc) cost[rI * ldc + c] = ic;
+                    }
+                }
+                // supplies last: srem does not alias the lists, u and cmask (which do) are cleared by the solver
+                for (int i = lane; i < mm; i += kWarp) srem[i] = i < nrow ? rowL[i] >> 8 : diff;
+                __syncwarp();
+                opt = transport_solve_wide<KC>(mm, ncc, krp, cost, flow, u, srem, deficit, cmask, rpred, way, cany, lane);
+            }
+        }
+        if (zero_matrix) {                                           // S4: all-zero distance matrix
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
             __syncwarp();
-            opt = transport_solve_wide<KC>(mm, ncc, krp, cost, flow, u, srem, deficit, cmask, rpred, way, cany, lane);
+            continue;
         }
         if (lane == 0) {
             double dist = opt < 0 ? __longlong_as_double(0x7ff8000000000000LL) : (double)opt;

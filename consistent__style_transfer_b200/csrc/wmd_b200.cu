@@ -77,8 +77,34 @@ struct Workspace {
     DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
     DevBuf counters;                            // kCounterBytes: work-claim counters, stage / list counts
     DevBuf biglist;                             // table mode: pairs the fused kernel leaves to the general path
+    // The wide solver classes of one chunk run side by side, each on its own stream with its own cost / flow scratch:
+    // one launch per class in sequence would pay one tail per class, and a pair of the larger classes runs for milliseconds.
+    DevBuf wscratch[8];
+    cudaStream_t wstream[8] = {};
+    cudaEvent_t wfork = nullptr, wjoin[8] = {};
+    int ensure_wide_streams()
+    {
+        if (wfork) return WMD_OK;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // hi = the numerically smallest = most urgent priority
+        for (int k = 0; k < 8; ++k) {
+            const int prio = std::max(hi, lo - k);                      // the larger the class, the earlier its blocks are placed
+            if (cudaStreamCreateWithPriority(&wstream[k], cudaStreamNonBlocking, prio) != cudaSuccess) return fail(WMD_ECUDA, "cudaStreamCreateWithPriority failed");
+            if (cudaEventCreateWithFlags(&wjoin[k], cudaEventDisableTiming) != cudaSuccess) return fail(WMD_ECUDA, "cudaEventCreate failed");
+        }
+        if (cudaEventCreateWithFlags(&wfork, cudaEventDisableTiming) != cudaSuccess) return fail(WMD_ECUDA, "cudaEventCreate failed");
+        return WMD_OK;
+    }
     void release()
     {
+        for (int k = 0; k < 8; ++k) {
+            wscratch[k].release();
+            if (wstream[k]) cudaStreamDestroy(wstream[k]);
+            if (wjoin[k]) cudaEventDestroy(wjoin[k]);
+            wstream[k] = nullptr; wjoin[k] = nullptr;
+        }
+        if (wfork) cudaEventDestroy(wfork);
+        wfork = nullptr;
         DevBuf *all[] = { &ids1, &ids2, &off1, &off2, &rows1, &cnt1, &ip1, &rows2, &cnt2, &ip2, &u12, &meta, &pqn,
                           &extra, &maxc, &tiles, &out, &status, &scratch, &plan, &wt1, &wt2, &lb, &l1, &l2, &am1, &am2, &counters, &biglist };
         for (DevBuf *b : all) b->release();
@@ -89,11 +115,11 @@ struct ProfRec { int kind; cudaEvent_t a, b; };
 
 // unsigned slots of Workspace::counters
 constexpr size_t kCounterBytes = 128;
-constexpr int kCtrFused = 10;                   // fused kernel's work-claim counter (slots 1..6: the solver classes)
-constexpr int kCtrNBig = 11;                    // length of Workspace::biglist
-constexpr int kCtrCost = 8;                     // general cost kernel's claim counter
-constexpr int kCtrStages = 9;                   // planned stages of the fast cost path
-constexpr int kCtrDmax = 12;                    // largest entry of the word-distance table (float bits)
+constexpr int kCtrFused = 18;                   // fused kernel's work-claim counter (slots 1..9: the solver classes)
+constexpr int kCtrNBig = 19;                    // length of Workspace::biglist
+constexpr int kCtrCost = 16;                    // general cost kernel's claim counter
+constexpr int kCtrStages = 17;                  // planned stages of the fast cost path
+constexpr int kCtrDmax = 20;                    // largest entry of the word-distance table (float bits)
 
 }  // namespace
 
@@ -130,6 +156,8 @@ struct wmd_engine {
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
     int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
+    int wide_small_minb = 8;                     // experiment: WMD_WIDE_SMALL_MINB=6
+    int wide_cap = 0;                            // WMD_WIDE_CAP: cap on resident blocks per SM of the wide solver classes KC >= 5 (0 = what fits)
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
@@ -375,13 +403,12 @@ int launch_cost(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1,
 
 // K3 launches of one chunk: one launch per solver class over all pairs of the chunk, or (list mode) over the pairs the
 // fused kernel left behind.  gather: costs come from the word-distance table instead of cost tiles.
-struct WideClass { int cls, kc, min_ml; };                      // instance (column words of the shorter side) and the shortest longest
-constexpr WideClass kWideClasses[] = {                          // document of a chunk that can produce a problem of the class
-    { kClsW1, 1, 32 }, { kClsW2, 2, 33 }, { kClsW3, 3, 65 }, { kClsW4, 4, 97 }, { kClsW6, 6, 129 }, { kClsW8, 8, 193 },
-};
+// shortest longest document of a chunk that can produce a residual problem of KC column words: the shorter side has more
+// than 32 (KC - 1) nodes (KC = 1: the longer side more than 32, one of which may be the dummy)
+inline int wide_min_ml(int kc) { return kc == 1 ? 32 : 32 * (kc - 1) + 1; }
 
 template <class K>
-int launch_wide_solver(wmd_engine *E, Workspace &W, cudaStream_t st, K kernel, SolveArgs &S, size_t per_warp, int32_t Bc)
+int launch_wide_solver(wmd_engine *E, DevBuf &scratch, cudaStream_t st, K kernel, SolveArgs &S, size_t per_warp, int32_t Bc)
 {
     int rc;
     const int wpb = 4;
@@ -390,10 +417,10 @@ int launch_wide_solver(wmd_engine *E, Workspace &W, cudaStream_t st, K kernel, S
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, wpb * 32, smem));
     if (nb < 1) return fail(WMD_ECUDA, "solver class %d cannot be resident", S.cls);
+    if (S.blocks_cap > 0) nb = std::min(nb, S.blocks_cap);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + wpb - 1) / wpb, (int64_t)E->sm_count * nb));
-    if ((rc = W.scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;      // per warp: quantised costs + flow
-    S.scratch = W.scratch.as<int32_t>();
-    Prof pr(E, WMD_K_SOLVE, st);
+    if ((rc = scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;        // per warp: quantised costs + flow
+    S.scratch = scratch.as<int32_t>();
     kernel<<<grid, wpb * 32, smem, st>>>(S);
     CK(cudaGetLastError());
     return WMD_OK;
@@ -412,6 +439,40 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
     S.list = list; S.nlist = nlist;
     S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
     S.scratch = nullptr;
+    // Fork: the wide classes (largest first) each on their own stream, class A on the chunk's stream next to them.
+    const bool wide = ML >= wide_min_ml(1);
+    Prof pr(E, WMD_K_SOLVE, st);
+    if (wide) {
+        if ((rc = W.ensure_wide_streams())) return rc;
+        CK(cudaEventRecord(W.wfork, st));
+    }
+    // Larger problems, largest class first.  The per-launch capacity follows the chunk's longest document; the instance
+    // only depends on the pair's own shorter side.
+    for (int kc = 8; kc >= 1; --kc) {
+        if (ML < wide_min_ml(kc)) continue;           // no document of the chunk is long enough for a problem of this class
+        S.cls = kClsW1 + kc - 1;
+        S.mr = std::min(kc == 8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1); S.mc = 32 * kc; S.ldc = 32 * kc;
+        S.counter = W.counters.as<unsigned int>() + S.cls;
+        S.blocks_cap = kc >= 5 ? E->wide_cap : 0;
+        cudaStream_t ws = W.wstream[kc - 1];
+        CK(cudaStreamWaitEvent(ws, W.wfork, 0));
+#define WMD_WIDE(KC, MINB)                                                                                                           \
+        (gather ? launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, true, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc)      \
+                : launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, false, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc))
+        switch (kc) {
+        case 1: rc = E->wide_small_minb == 6 ? WMD_WIDE(1, 6) : WMD_WIDE(1, 8); break;
+        case 2: rc = E->wide_small_minb == 6 ? WMD_WIDE(2, 6) : WMD_WIDE(2, 8); break;
+        case 3: rc = WMD_WIDE(3, 6); break;
+        case 4: rc = WMD_WIDE(4, 6); break;
+        case 5: rc = WMD_WIDE(5, 5); break;
+        case 6: rc = WMD_WIDE(6, 5); break;
+        case 7: rc = WMD_WIDE(7, 4); break;
+        default: rc = WMD_WIDE(8, 4); break;
+        }
+#undef WMD_WIDE
+        if (rc) return rc;
+        CK(cudaEventRecord(W.wjoin[kc - 1], ws));
+    }
     {                                                 // class A: both sides of the residual problem fit one word
         S.cls = kClsA;
         S.mr = S.mc = std::min(32, ML + 1);           // class A may turn the problem round: the dummy then is a row
@@ -421,7 +482,6 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         const size_t smem = solve_small_smem_per_warp(S.mr, S.mc, S.ldc) * wpb;
         const int blocks_per_sm = E->solve_blocks_per_sm * 2;                         // __launch_bounds__(128, 9)
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * blocks_per_sm));
-        Prof pr(E, WMD_K_SOLVE, st);
         if (gather) {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(emd_solve_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             emd_solve_small_kernel<true><<<grid, wpb * 32, smem, st>>>(S);
@@ -431,28 +491,8 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         }
         CK(cudaGetLastError());
     }
-    // Larger problems, largest class first.  The per-launch capacity follows the chunk's longest document (rows: one more
-    // for the dummy row); the instance only depends on the pair's own shorter side.
-    for (int ci = (int)(sizeof kWideClasses / sizeof kWideClasses[0]) - 1; ci >= 0; --ci) {
-        const WideClass &C = kWideClasses[ci];
-        if (ML < C.min_ml) continue;                  // no document of the chunk is long enough for a problem of this class
-        S.cls = C.cls;
-        S.mr = std::min(C.cls == kClsW8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1); S.mc = 32 * C.kc; S.ldc = 32 * C.kc;
-        S.counter = W.counters.as<unsigned int>() + C.cls;
-#define WMD_WIDE(KC, MINB)                                                                                                           \
-        (gather ? launch_wide_solver(E, W, st, emd_solve_wide_kernel<KC, true, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc)      \
-                : launch_wide_solver(E, W, st, emd_solve_wide_kernel<KC, false, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc))
-        switch (C.kc) {
-        case 1: rc = WMD_WIDE(1, 8); break;
-        case 2: rc = WMD_WIDE(2, 8); break;
-        case 3: rc = WMD_WIDE(3, 6); break;
-        case 4: rc = WMD_WIDE(4, 6); break;
-        case 6: rc = WMD_WIDE(6, 5); break;
-        default: rc = WMD_WIDE(8, 4); break;
-        }
-#undef WMD_WIDE
-        if (rc) return rc;
-    }
+    for (int kc = 8; wide && kc >= 1; --kc)            // join
+        if (ML >= wide_min_ml(kc)) CK(cudaStreamWaitEvent(st, W.wjoin[kc - 1], 0));
     return WMD_OK;
 }
 
@@ -733,6 +773,8 @@ int enqueue_host_job(wmd_engine *E, const HostJob &J)
 // caller's buffers that are already queued must have landed before the call reports its error.
 int drain_streams(wmd_engine *E)
 {
+    for (Workspace &W : E->ws)                          // an error exit between fork and join leaves the class streams on their own
+        for (cudaStream_t ws : W.wstream) if (ws) cudaStreamSynchronize(ws);
     const cudaError_t e0 = cudaStreamSynchronize(E->streams[0]), e1 = cudaStreamSynchronize(E->streams[1]);
     E->slot_used[0] = E->slot_used[1] = false;
     if (e0 != cudaSuccess || e1 != cudaSuccess)
@@ -1147,6 +1189,7 @@ size_t workspace_resident(const Workspace &W)
                             &W.counters, &W.biglist };
     size_t t = 0;
     for (const DevBuf *b : all) t += b->cap;
+    for (const DevBuf &b : W.wscratch) t += b.cap;
     return t;
 }
 
@@ -1195,6 +1238,8 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
             if (sscanf(v, "%d,%d", &a, &b) == 2 && a >= 1024 && b >= a) { E->host_chunk_first = a; E->host_chunk_max = std::min(b, 1 << 20); }
         }
         if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
+        if (const char *v = getenv("WMD_WIDE_CAP")) E->wide_cap = std::max(0, atoi(v));
+        if (const char *v = getenv("WMD_WIDE_SMALL_MINB")) E->wide_small_minb = atoi(v);
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));

@@ -142,7 +142,7 @@ def test_length_sweep_matches_oracle(eng_mod, oracle, L, dtab):
 
 @pytest.mark.parametrize("shape,variant,V,d,B", [
     # long documents over small vocabularies: unequal masses, partial cancellation, tied costs, residual problems
-    # of every solver class (A <= 32, B <= 64, C <= 256 rows) and packed as well as block-split cost stages in one launch
+    # of every solver class (A and the wide instances) and packed as well as block-split cost stages in one launch
     ("uniform:1-90", "independent", 3000, 300, 1500), ("uniform:1-256", "independent", 400, 64, 600), ("fixed:256", "independent", 300, 8, 200),
     ("uniform:30-70", "noised", 150, 100, 800), ("fixed:100", "independent", 120, 32, 500),
     ("fixed:200", "noised", 5000, 16, 300), ("uniform:40-45", "independent", 10000, 300, 1000),
@@ -172,7 +172,7 @@ def _chain_table(n, eps=0.002, h=0.2, d=8):
 
 @pytest.mark.parametrize("n", [12, 31, 33, 64, 100, 200, 256])
 def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n, dtab):
-    # paths longer than 32 hops are walked in pieces by the class B / C solver (solve.cuh: transport_solve_multi)
+    # paths longer than 32 hops are walked in pieces by the wide solver (solve_wide.cuh: transport_solve_wide)
     table = _chain_table(n)
     fwd = (np.arange(1, n + 1), n + 1 + np.arange(0, n))
     docs1, docs2 = [], []
@@ -188,6 +188,42 @@ def test_long_augmenting_paths_match_oracle(eng_mod, oracle, n, dtab):
     e = eng_mod.WMDEngine(table, distance_table=dtab)
     got, st = e.wmd_pairs(ids1, off1, ids2, off2)
     want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=4)
+    _assert_wmd_equal(got, st, want, wst)
+    assert np.array_equal(got, want)
+    e.close()
+
+
+def test_wide_solver_shapes_match_oracle(eng_mod, oracle, dtab):
+    # solve_wide.cuh: every instance (column words of the shorter side 1 .. 8), both orientations (the supplying side the
+    # longer or the shorter one), the 257-row case (256 nodes a side plus the dummy), heavy cancellation (nodes without
+    # residual mass still count for maxC)
+    V = 700
+    table = workload.make_table(V, 12, seed=5)
+    rng = np.random.default_rng(17)
+    docs1, docs2 = [], []
+    for long_n in (33, 64, 65, 100, 129, 161, 193, 225, 256):
+        for short_n in (1, 9, 31, 33, 64, 97, 128, 160, 192, 224, 256):
+            if short_n > long_n:
+                continue
+            a = rng.choice(V, size=long_n, replace=False)
+            b = rng.choice(V, size=short_n, replace=False)
+            if (long_n + short_n) % 3 == 0:                      # shared tokens: cancellation on both sides
+                k = min(short_n, long_n) // 2
+                b[:k] = a[:k]
+            if (long_n + short_n) % 4 == 1:                      # repeated tokens: unequal masses
+                b = np.concatenate([b, b[:min(len(b), 256 - len(b))][:7]])
+            for x, y in ((a, b), (b, a)):
+                docs1.append(x.astype(np.int32)); docs2.append(y.astype(np.int32))
+    full = rng.permutation(V)[:512]
+    docs1.append(full[:256].astype(np.int32)); docs2.append(full[256:].astype(np.int32))                 # 256 x 256, equal masses
+    docs1.append(np.concatenate([full[:255], full[:1]]).astype(np.int32)); docs2.append(full[256:].astype(np.int32))      # 255 x 256 + dummy
+    docs1.append(full[:256].astype(np.int32)); docs2.append(np.concatenate([full[256:511], full[256:257]]).astype(np.int32))
+    docs1.append(full[:256].astype(np.int32)); docs2.append(full[100:356].astype(np.int32))              # 156 shared tokens
+    ids1, off1 = workload.to_csr(docs1)
+    ids2, off2 = workload.to_csr(docs2)
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
+    got, st = e.wmd_pairs(ids1, off1, ids2, off2)
+    want, wst = oracle.batch_wmd(table, ids1, off1, ids2, off2, nthreads=8)
     _assert_wmd_equal(got, st, want, wst)
     assert np.array_equal(got, want)
     e.close()
