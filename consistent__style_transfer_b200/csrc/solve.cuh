@@ -28,7 +28,7 @@ struct SolveArgs {
     int32_t cls;                      // class this launch serves (kClsA also finalises kClsNone pairs with status 0)
     int32_t mr, mc;                   // row / column capacity of the per-warp matrices
     int32_t ldc;                      // column pitch (odd)
-    int32_t blocks_cap;               // host side only: cap on resident blocks per SM (0 = what fits)
+    int32_t _pad;
     int32_t *scratch;                 // wide classes: [warps, 2 * mr * ldc] quantised costs + flow
     const int32_t *ip1, *ip2;
     const int32_t *u12, *meta;

@@ -157,7 +157,6 @@ struct wmd_engine {
     int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
     int wide_small_minb = 8;                     // experiment: WMD_WIDE_SMALL_MINB=6
-    int wide_cap = 0;                            // WMD_WIDE_CAP: cap on resident blocks per SM of the wide solver classes KC >= 5 (0 = what fits)
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
@@ -417,7 +416,6 @@ int launch_wide_solver(wmd_engine *E, DevBuf &scratch, cudaStream_t st, K kernel
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, wpb * 32, smem));
     if (nb < 1) return fail(WMD_ECUDA, "solver class %d cannot be resident", S.cls);
-    if (S.blocks_cap > 0) nb = std::min(nb, S.blocks_cap);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + wpb - 1) / wpb, (int64_t)E->sm_count * nb));
     if ((rc = scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;        // per warp: quantised costs + flow
     S.scratch = scratch.as<int32_t>();
@@ -439,8 +437,10 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
     S.list = list; S.nlist = nlist;
     S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
     S.scratch = nullptr;
-    // Fork: the wide classes (largest first) each on their own stream, class A on the chunk's stream next to them.
-    const bool wide = ML >= wide_min_ml(1);
+    // Fork: the wide classes (largest first) each on their own stream, class A on the chunk's stream next to them.  Chunks
+    // whose longest document allows two wide classes at most (<= 64 tokens) stay on the chunk's stream: their pairs are
+    // short-lived, and the kernels measured slower side by side (64-token pairs 15.9 -> 18.2 ms per 2^18).
+    const bool wide = ML >= wide_min_ml(3);
     Prof pr(E, WMD_K_SOLVE, st);
     if (wide) {
         if ((rc = W.ensure_wide_streams())) return rc;
@@ -453,9 +453,8 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         S.cls = kClsW1 + kc - 1;
         S.mr = std::min(kc == 8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1); S.mc = 32 * kc; S.ldc = 32 * kc;
         S.counter = W.counters.as<unsigned int>() + S.cls;
-        S.blocks_cap = kc >= 5 ? E->wide_cap : 0;
-        cudaStream_t ws = W.wstream[kc - 1];
-        CK(cudaStreamWaitEvent(ws, W.wfork, 0));
+        cudaStream_t ws = wide ? W.wstream[kc - 1] : st;
+        if (wide) CK(cudaStreamWaitEvent(ws, W.wfork, 0));
 #define WMD_WIDE(KC, MINB)                                                                                                           \
         (gather ? launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, true, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc)      \
                 : launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, false, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc))
@@ -471,7 +470,7 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         }
 #undef WMD_WIDE
         if (rc) return rc;
-        CK(cudaEventRecord(W.wjoin[kc - 1], ws));
+        if (wide) CK(cudaEventRecord(W.wjoin[kc - 1], ws));
     }
     {                                                 // class A: both sides of the residual problem fit one word
         S.cls = kClsA;
@@ -1238,7 +1237,6 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
             if (sscanf(v, "%d,%d", &a, &b) == 2 && a >= 1024 && b >= a) { E->host_chunk_first = a; E->host_chunk_max = std::min(b, 1 << 20); }
         }
         if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
-        if (const char *v = getenv("WMD_WIDE_CAP")) E->wide_cap = std::max(0, atoi(v));
         if (const char *v = getenv("WMD_WIDE_SMALL_MINB")) E->wide_small_minb = atoi(v);
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
