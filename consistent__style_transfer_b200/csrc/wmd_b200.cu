@@ -156,7 +156,6 @@ struct wmd_engine {
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
     int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
-    int wide_small_minb = 8;                     // experiment: WMD_WIDE_SMALL_MINB=6
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
@@ -459,8 +458,8 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         (gather ? launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, true, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc)      \
                 : launch_wide_solver(E, W.wscratch[KC - 1], ws, emd_solve_wide_kernel<KC, false, MINB>, S, solve_wide_smem_per_warp<KC>(S.mr), Bc))
         switch (kc) {
-        case 1: rc = E->wide_small_minb == 6 ? WMD_WIDE(1, 6) : WMD_WIDE(1, 8); break;
-        case 2: rc = E->wide_small_minb == 6 ? WMD_WIDE(2, 6) : WMD_WIDE(2, 8); break;
+        case 1: rc = WMD_WIDE(1, 8); break;
+        case 2: rc = WMD_WIDE(2, 8); break;
         case 3: rc = WMD_WIDE(3, 6); break;
         case 4: rc = WMD_WIDE(4, 6); break;
         case 5: rc = WMD_WIDE(5, 5); break;
@@ -1237,7 +1236,6 @@ int wmd_create(const float *table_host, int64_t V, int32_t d, int64_t row_stride
             if (sscanf(v, "%d,%d", &a, &b) == 2 && a >= 1024 && b >= a) { E->host_chunk_first = a; E->host_chunk_max = std::min(b, 1 << 20); }
         }
         if (const char *v = getenv("WMD_AP_R1MULT")) E->ap_r1_mult = std::max(1, atoi(v));
-        if (const char *v = getenv("WMD_WIDE_SMALL_MINB")) E->wide_small_minb = atoi(v);
         if (const char *v = getenv("WMD_FUSED_MINB")) E->fused_minb = std::max(8, std::min(10, atoi(v)));
     }
     if (cudaMalloc(&E->table, (size_t)V * E->ld * 4) != cudaSuccess) return bail(fail(WMD_ENOMEM, "cudaMalloc table failed"));
