@@ -1440,9 +1440,12 @@ int wmd_workspace_bytes(wmd_handle E, int64_t npairs, int32_t max_len1, int32_t 
                 per += (size_t)Bc * ml1 * ml2 * 4;                                       // cost tiles
                 per += (size_t)plan_stage_bound(Bc, ml1, ml2, Bc * (int64_t)ml1, Bc * (int64_t)ml2, std::max(E->fast_R, 8), kStageTilesMax) * sizeof(StageRec);
             }
-            if (ML >= 32) {                                                              // wide solver scratch: costs + flow per resident warp
-                const int kc = std::min((ML + 31) / 32, 8);                              // (upper bound: 32 warps per SM up to <2>, 24 / 20 / 16 above)
-                per += (size_t)E->sm_count * (kc <= 2 ? 32 : kc <= 4 ? 24 : kc <= 6 ? 20 : 16) * 2 * (size_t)(std::min(ML, kMaxDocLen) + 1) * (32 * (kc == 5 ? 6 : kc == 7 ? 8 : kc)) * 4;
+            for (int kc = 1; kc <= 8; ++kc) {                                            // wide solver scratch: costs + flow per resident warp, per class
+                if (ML < wide_min_ml(kc)) continue;
+                static const int blocks[8] = { 8, 8, 6, 6, 5, 5, 4, 4 };                 // resident blocks per SM (__launch_bounds__ of the instances)
+                const size_t warps = std::min<size_t>((size_t)E->sm_count * blocks[kc - 1] * 4, (size_t)((Bc + 3) / 4) * 4);
+                const size_t mr = (size_t)std::min(kc == 8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1);
+                per += warps * 2 * mr * (32 * kc) * 4;
             }
         }
         *estimate = (int64_t)(fixed + (size_t)slots * per);
