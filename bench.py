@@ -259,6 +259,10 @@ class Ctx:
         torch = self.torch
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.numa = None
+        if self.world > 1 and os.environ.get("WMD_NUMA_BIND", "1") != "0":
+            from consistent__style_transfer_b200 import sharding
+            self.numa = sharding.bind_host_to_gpu(self.local)          # before any pinned buffer exists
         if self.world > 1 and not self.dist.is_initialized():
             self.dist.init_process_group("nccl", device_id=self.dev)
         self.table = workload.make_table(self.a.vocab, d or self.a.d, seed=0)
@@ -464,7 +468,8 @@ def pairs_arm(ctx, cpu):
                               "sharding.wmd_pairs_sharded -- H2D of the rank's slice, kernels, NCCL gather of all scores on every "
                               "device -- + device->host read of the rank's own slice, so the global result reaches host memory once), "
                               "max over ranks",
-                    "matches_device_path": main["same"]},
+                    "matches_device_path": main["same"],
+                    "host_binding": ctx.numa},                            # N > 1: rank 0's CPU affinity / NUMA node (sharding.bind_host_to_gpu)
             "gpu_launches": launches,
             "roofline": roofline,
             "word_distance_table": {"enabled": tinfo["enabled"], "bytes": tinfo["bytes"], "table_build_ms": tinfo["build_ms"],

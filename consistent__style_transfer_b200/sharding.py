@@ -73,6 +73,42 @@ def csr_slice(ids: np.ndarray, off: np.ndarray, lo: int, hi: int) -> Tuple[np.nd
     return np.ascontiguousarray(ids[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo])
 
 
+def parse_cpulist(text: str) -> set:
+    """'0-3,8,10-11' -> {0, 1, 2, 3, 8, 10, 11} (the format of sysfs local_cpulist / cpuset files)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int, sysfs: str = "/sys/bus/pci/devices") -> Optional[dict]:
+    """One process per GPU: run this rank's host threads on the CPUs of the NUMA node its GPU hangs off, BEFORE pinned
+    staging buffers are allocated (first touch puts them on that node).  Every rank of a multi-GPU host job copies its
+    slice host -> device at the same time; with the pages on the far socket those copies cross the inter-socket link
+    and the end-to-end step, unlike the kernels, stops scaling.  Returns what was done (None when the topology is not
+    visible or the node's CPUs are outside this process's cpuset -- then nothing changes)."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, bdf, "local_cpulist")) as f:
+            local = parse_cpulist(f.read())
+        with open(os.path.join(sysfs, bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return {"bdf": bdf, "numa_node": node, "bound": False, "cpus": len(allowed)}
+        os.sched_setaffinity(0, cpus)
+        return {"bdf": bdf, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

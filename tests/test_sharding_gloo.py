@@ -92,3 +92,13 @@ def test_partition_by_tokens_matches_the_linear_cost_model():
         v = sharding.partition_by_tokens(off1[5000:15001], off2[5000:15001], world)
         assert v[-1] == 10_000 and np.all(np.diff(v) >= 0)
     assert list(sharding.partition_by_tokens(np.zeros(1, np.int64), np.zeros(1, np.int64), 3)) == [0, 0, 0, 0]
+
+
+def test_parse_cpulist_and_binding_without_a_gpu():
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding.parse_cpulist("") == set()
+    # no CUDA device / no sysfs entry: nothing changes, nothing raises
+    import os
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_host_to_gpu(0, sysfs="/nonexistent") is None
+    assert os.sched_getaffinity(0) == before

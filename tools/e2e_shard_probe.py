@@ -7,6 +7,7 @@ from consistent__style_transfer_b200.engine import WMDEngine
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
+numa = sharding.bind_host_to_gpu(local) if os.environ.get("WMD_NUMA_BIND", "1") != "0" else None
 dist.init_process_group("nccl", device_id=dev)
 table = workload.make_table(10000, 300, seed=0)
 eng = WMDEngine(table, device=local)
@@ -27,6 +28,9 @@ for it in range(8):
     t0 = time.perf_counter(); g_out, g_st = sharding.gather_scores(out, st, bounds); tick("gather", t0)
     t0 = time.perf_counter(); h_out[lo:hi].copy_(g_out[lo:hi], non_blocking=True); h_st[lo:hi].copy_(g_st[lo:hi], non_blocking=True); tick("d2h", t0)
     T["total"] = T.get("total", 0.0) + time.perf_counter() - t_all
+res = [None] * world
+dist.all_gather_object(res, ({k: round(v / 5 * 1e3, 3) for k, v in T.items()}, numa))
 if rank == 0:
-    print({k: round(v / 5 * 1e3, 3) for k, v in T.items()})
+    for r, x in enumerate(res):
+        print(r, x)
 dist.destroy_process_group()
