@@ -28,6 +28,7 @@ __host__ __device__ inline int solver_class(int m, int nc)
     if (hi > kMaxDocLen) return kClsW8;                          // 256 nodes a side plus the dummy: the one launch with 257 rows
     return kClsW1 + ((lo + 31) >> 5) - 1;
 }
+constexpr int kMetaWorkShift = 8;        // bits 8 .. 15: work estimate of the pair, min(255, rows x columns / 256) (longest-first order)
 constexpr int kMetaSwap = 16;            // doc2 is the heavier (supplying) side
 
 // One side of a batch of documents. CSR (off != nullptr) or padded [npairs, L] (off == nullptr).

@@ -190,7 +190,7 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
         const int m = swap ? nQ : nP;
         const int nc = (swap ? nP : nQ) + ((sP != sQ) ? 1 : 0);
         const int cls = solver_class(m, nc);
-        meta = cls | (swap ? kMetaSwap : 0);
+        meta = cls | (swap ? kMetaSwap : 0) | (min(255, (m * nc) >> 8) << kMetaWorkShift);
         if (lane == 0) {
             w.u12[q] = u1 | (u2 << 16);
             w.meta[q] = meta;

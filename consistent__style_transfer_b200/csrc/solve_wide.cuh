@@ -25,15 +25,18 @@
 
 namespace wmd {
 
-// per-warp shared memory: u, srem [mrp] ints, deficit [32 KC] ints, cmask [32 KC * krp] words, rpred [mrp] + way, cany [32 KC] shorts
+// per-warp shared memory: u [mrp] ints, deficit [32 KC] ints, cmask [32 KC * krp] words, rpred [mrp] + way, cany [32 KC] shorts
+// per-warp global scratch: cost, flow [mr * 32 KC] ints, srem [mrp] ints (read once per row: it would cost the 5- and
+// 6-word classes their sixth block per SM in shared memory)
 __host__ __device__ inline int wide_krp(int mr) { return (mr + 31) >> 5; }
 template <int KC>
 __host__ __device__ inline size_t solve_wide_smem_per_warp(int mr)
 {
     const size_t krp = (size_t)wide_krp(mr), mrp = 32 * krp, mcp = 32 * KC;
-    const size_t bytes = 4 * (2 * mrp + mcp + mcp * krp) + 2 * (mrp + 2 * mcp);
+    const size_t bytes = 4 * (mrp + mcp + mcp * krp) + 2 * (mrp + 2 * mcp);
     return (bytes + 15) & ~(size_t)15;
 }
+__host__ __device__ inline size_t solve_wide_scratch_ints_per_warp(int mr, int ldc) { return (size_t)2 * mr * ldc + 32 * (size_t)wide_krp(mr); }
 
 template <int KC>
 __device__ long long transport_solve_wide(const int mm, const int ncc, const int krp, const int *__restrict__ cost, int *__restrict__ flow,
@@ -275,6 +278,39 @@ __device__ long long transport_solve_wide(const int mm, const int ncc, const int
     return warp_sum_ll(tot);
 }
 
+// Longest first: the pairs of a chunk in descending order of their work estimate (meta bits 8 .. 15), one counting sort in
+// a single block.  A pair of the larger classes runs for milliseconds; claimed in arrival order the longest ones may start
+// last and the chunk waits for them with most of the SMs idle.
+struct ListSortArgs {
+    const int32_t *list;              // pairs to order (launch-local indices), or nullptr: 0 .. npairs - 1
+    const unsigned int *nlist;        // its length on the device, or nullptr: npairs
+    int32_t npairs;
+    const int32_t *meta;
+    int32_t *sorted;
+};
+__global__ void __launch_bounds__(1024)
+list_sort_kernel(const __grid_constant__ ListSortArgs A)
+{
+    __shared__ unsigned int hist[256], cur[256];
+    const int n = A.nlist ? (int)*A.nlist : A.npairs;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int q = A.list ? A.list[i] : i;
+        atomicAdd(&hist[(A.meta[q] >> kMetaWorkShift) & 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int k = 255; k >= 0; --k) { cur[k] = run; run += hist[k]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int q = A.list ? A.list[i] : i;
+        A.sorted[atomicAdd(&cur[(A.meta[q] >> kMetaWorkShift) & 255], 1u)] = q;
+    }
+}
+
 template <int KC, bool GATHER, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
@@ -284,15 +320,15 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int krp = wide_krp(A.mr), mrp = 32 * krp;
     unsigned char *sb = smem_w + (size_t)wib * solve_wide_smem_per_warp<KC>(A.mr);
-    int *u = reinterpret_cast<int *>(sb), *srem = u + mrp, *deficit = srem + mrp;
+    int *u = reinterpret_cast<int *>(sb), *deficit = u + mrp;
     unsigned *cmask = reinterpret_cast<unsigned *>(deficit + ldc);
     short *rpred = reinterpret_cast<short *>(cmask + (size_t)ldc * krp), *way = rpred + mrp;
     unsigned short *cany = reinterpret_cast<unsigned short *>(way + ldc);
     int *listR = u, *listC = reinterpret_cast<int *>(cmask);         // compaction lists: dead before the solver clears u / cmask
-    int *cost, *flow;
+    int *cost, *flow, *srem;
     {
         const size_t w = (size_t)blockIdx.x * wpb + wib, mat = (size_t)A.mr * ldc;
-        cost = A.scratch + w * 2 * mat; flow = cost + mat;
+        cost = A.scratch + w * solve_wide_scratch_ints_per_warp(A.mr, ldc); flow = cost + mat; srem = flow + mat;
     }
     int64_t tok1, tok2;
     { int l; doc_span(A.s1, A.p0, tok1, l); doc_span(A.s2, A.p0, tok2, l); }

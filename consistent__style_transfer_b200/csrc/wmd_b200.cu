@@ -77,6 +77,7 @@ struct Workspace {
     DevBuf lb, l1, l2, am1, am2;                // rwmd outputs (host entry)
     DevBuf counters;                            // kCounterBytes: work-claim counters, stage / list counts
     DevBuf biglist;                             // table mode: pairs the fused kernel leaves to the general path
+    DevBuf sorted;                              // the chunk's pairs, longest first (list_sort_kernel)
     // The wide solver classes of one chunk run side by side, each on its own stream with its own cost / flow scratch:
     // one launch per class in sequence would pay one tail per class, and a pair of the larger classes runs for milliseconds.
     DevBuf wscratch[8];
@@ -97,6 +98,7 @@ struct Workspace {
     }
     void release()
     {
+        sorted.release();
         for (int k = 0; k < 8; ++k) {
             wscratch[k].release();
             if (wstream[k]) cudaStreamDestroy(wstream[k]);
@@ -416,7 +418,7 @@ int launch_wide_solver(wmd_engine *E, DevBuf &scratch, cudaStream_t st, K kernel
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, wpb * 32, smem));
     if (nb < 1) return fail(WMD_ECUDA, "solver class %d cannot be resident", S.cls);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + wpb - 1) / wpb, (int64_t)E->sm_count * nb));
-    if ((rc = scratch.ensure((size_t)grid * wpb * 2 * S.mr * S.ldc * 4))) return rc;        // per warp: quantised costs + flow
+    if ((rc = scratch.ensure((size_t)grid * wpb * solve_wide_scratch_ints_per_warp(S.mr, S.ldc) * 4))) return rc;      // per warp: quantised costs + flow + supplies
     S.scratch = scratch.as<int32_t>();
     kernel<<<grid, wpb * 32, smem, st>>>(S);
     CK(cudaGetLastError());
@@ -442,7 +444,12 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
     const bool wide = ML >= wide_min_ml(3);
     Prof pr(E, WMD_K_SOLVE, st);
     if (wide) {
-        if ((rc = W.ensure_wide_streams())) return rc;
+        if ((rc = W.ensure_wide_streams()) || (rc = W.sorted.ensure((size_t)Bc * 4))) return rc;
+        ListSortArgs L;
+        L.list = list; L.nlist = nlist; L.npairs = Bc; L.meta = pw.meta; L.sorted = W.sorted.as<int32_t>();
+        list_sort_kernel<<<1, 1024, 0, st>>>(L);
+        CK(cudaGetLastError());
+        S.list = L.sorted;
         CK(cudaEventRecord(W.wfork, st));
     }
     // Larger problems, largest class first.  The per-launch capacity follows the chunk's longest document; the instance
@@ -462,10 +469,10 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         case 2: rc = WMD_WIDE(2, 8); break;
         case 3: rc = WMD_WIDE(3, 6); break;
         case 4: rc = WMD_WIDE(4, 6); break;
-        case 5: rc = WMD_WIDE(5, 5); break;
-        case 6: rc = WMD_WIDE(6, 5); break;
-        case 7: rc = WMD_WIDE(7, 4); break;
-        default: rc = WMD_WIDE(8, 4); break;
+        case 5: rc = WMD_WIDE(5, 6); break;
+        case 6: rc = WMD_WIDE(6, 6); break;
+        case 7: rc = WMD_WIDE(7, 5); break;
+        default: rc = WMD_WIDE(8, 5); break;
         }
 #undef WMD_WIDE
         if (rc) return rc;
@@ -1188,6 +1195,7 @@ size_t workspace_resident(const Workspace &W)
     size_t t = 0;
     for (const DevBuf *b : all) t += b->cap;
     for (const DevBuf &b : W.wscratch) t += b.cap;
+    t += W.sorted.cap;
     return t;
 }
 
@@ -1442,10 +1450,10 @@ int wmd_workspace_bytes(wmd_handle E, int64_t npairs, int32_t max_len1, int32_t 
             }
             for (int kc = 1; kc <= 8; ++kc) {                                            // wide solver scratch: costs + flow per resident warp, per class
                 if (ML < wide_min_ml(kc)) continue;
-                static const int blocks[8] = { 8, 8, 6, 6, 5, 5, 4, 4 };                 // resident blocks per SM (__launch_bounds__ of the instances)
+                static const int blocks[8] = { 8, 8, 6, 6, 6, 6, 5, 5 };                 // resident blocks per SM (__launch_bounds__ of the instances)
                 const size_t warps = std::min<size_t>((size_t)E->sm_count * blocks[kc - 1] * 4, (size_t)((Bc + 3) / 4) * 4);
                 const size_t mr = (size_t)std::min(kc == 8 ? kMaxDocLen + 1 : kMaxDocLen, ML + 1);
-                per += warps * 2 * mr * (32 * kc) * 4;
+                per += warps * solve_wide_scratch_ints_per_warp((int)mr, 32 * kc) * 4;
             }
         }
         *estimate = (int64_t)(fixed + (size_t)slots * per);
