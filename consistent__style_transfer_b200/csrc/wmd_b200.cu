@@ -467,8 +467,8 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
         switch (kc) {
         case 1: rc = WMD_WIDE(1, 8); break;
         case 2: rc = WMD_WIDE(2, 8); break;
-        case 3: rc = WMD_WIDE(3, 6); break;
-        case 4: rc = WMD_WIDE(4, 6); break;
+        case 3: rc = WMD_WIDE(3, 8); break;
+        case 4: rc = WMD_WIDE(4, 8); break;
         case 5: rc = WMD_WIDE(5, 6); break;
         case 6: rc = WMD_WIDE(6, 6); break;
         case 7: rc = WMD_WIDE(7, 5); break;
