@@ -86,7 +86,8 @@ def config_dict(a, n_gpus):
             "cost": "float32 numpy-order (bit-exact)", "emd": "pyemd 1e6-grid integer optimum, exact",
             "l2": "256 MiB flush write between timed steps",
             "parallelism": f"pairs sharded over {n_gpus} GPU(s) in token-balanced contiguous slices; no data-path "
-                           f"collective, one NCCL gather of the float64 scores + status per step inside the timed region"}
+                           f"collective; every rank ends each step with all float64 scores + status on its device, inside the "
+                           f"timed region (stored by the kernels into the peers' copies over NVLink + a barrier, or one NCCL all-gather)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,6 +282,9 @@ class Ctx:
         return float(t.item())
 
     def close(self):
+        if getattr(self, "peer", None) is not None:
+            self.peer.close()
+            self.peer = None
         if self.eng is not None:
             self.eng.close()
         if self.world > 1 and self.dist.is_initialized():
@@ -324,7 +328,28 @@ def pairs_arm(ctx, cpu):
     d_st = torch.empty(nloc, dtype=torch.int32, device=dev)
     gathered = {}
 
+    # N > 1: the gather of the final scores (12 B/pair, the path's only exchange) is fused into the kernels -- every
+    # rank's kernels store their scores into the peers' copies of the global result over NVLink (sharding.PeerScores),
+    # a tiny all-reduce is the barrier.  WMD_PEER_GATHER=0 (or no CUDA IPC on the box): one NCCL all-gather instead.
+    peer = None
+    if world > 1 and os.environ.get("WMD_PEER_GATHER", "1") != "0":
+        try:
+            peer = sharding.PeerScores(eng, int(bounds[-1]))
+        except Exception as exc:                                           # noqa: BLE001 -- any failure: the NCCL path
+            sys.stderr.write(f"[bench] peer gather unavailable ({exc}); using the NCCL all-gather\n")
+    if world > 1:                                                          # every rank must take the same path
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        ctx.dist.all_reduce(ok, op=ctx.dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and peer is not None:
+            peer.close(); peer = None
+    ctx.peer = peer
+
     def dev_step():
+        if peer is not None:
+            g_out, g_st = peer.begin(lo)
+            eng.wmd_pairs_cuda(d_ids1, d_off1, d_ids2, d_off2, ml1, ml2, out=g_out[lo:hi], status=g_st[lo:hi])
+            gathered["out"], gathered["st"] = peer.end()
+            return
         eng.wmd_pairs_cuda(d_ids1, d_off1, d_ids2, d_off2, ml1, ml2, out=d_out, status=d_st)
         if world > 1:                                                      # the only exchange: final scores + status, 12 B/pair
             gathered["out"], gathered["st"] = sharding.gather_scores(d_out, d_st, bounds)
@@ -344,7 +369,7 @@ def pairs_arm(ctx, cpu):
         else:
             # every rank ends with ALL scores on its device (the product's contract) and reads its OWN slice back:
             # the global result reaches host memory exactly once per step
-            out, st, (a0, a1) = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, np_ids1, np_off1, np_ids2, np_off2)
+            out, st, (a0, a1) = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, np_ids1, np_off1, np_ids2, np_off2, peer=peer)
             h_out[a0:a1].copy_(out[a0:a1], non_blocking=True); h_st[a0:a1].copy_(st[a0:a1], non_blocking=True)
             gathered["e2e_out"] = out
             torch.cuda.synchronize()
@@ -373,6 +398,7 @@ def pairs_arm(ctx, cpu):
         prof_serial = eng.profile(reset=True)
         eng.set_profiling(False); eng.set_serial(False)
         total_ms_max = ctx.max_over_ranks(total_ms)
+        dev_snapshot = (gathered["out"] if world > 1 else d_out).clone()   # the peer buffer sets are reused by the e2e arm
         for _ in range(a.warmup):
             host_step()
         ctx.barrier()
@@ -385,7 +411,7 @@ def pairs_arm(ctx, cpu):
             e2e_s += time.perf_counter() - t0
         ctx.barrier()
         e2e_s = ctx.max_over_ranks(e2e_s)
-        dev_scores = (gathered["out"] if world > 1 else d_out).cpu().numpy()
+        dev_scores = dev_snapshot.cpu().numpy()
         if world > 1:                                                      # the e2e arm's gathered tensor against the device arm's
             same = bool(np.array_equal(gathered["e2e_out"].cpu().numpy(), dev_scores)) and bool(np.array_equal(np_out[lo:hi], dev_scores[lo:hi]))
         else:
@@ -471,6 +497,9 @@ def pairs_arm(ctx, cpu):
                     "matches_device_path": main["same"],
                     "host_binding": ctx.numa},                            # N > 1: rank 0's CPU affinity / NUMA node (sharding.bind_host_to_gpu)
             "gpu_launches": launches,
+            "score_gather": ("none (one GPU)" if world == 1 else
+                             "fused: the kernels store scores + status into the peers' copies over NVLink (CUDA IPC), barrier = one 4-byte all-reduce"
+                             if ctx.peer is not None else "one NCCL all-gather of scores + status after the kernels"),
             "roofline": roofline,
             "word_distance_table": {"enabled": tinfo["enabled"], "bytes": tinfo["bytes"], "table_build_ms": tinfo["build_ms"],
                                     "first_call_s": main["first_call_s"],

@@ -16,6 +16,8 @@ c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_f64p = ctypes.POINTER(ctypes.c_double)
 c_handle = ctypes.c_void_p
+IPC_HANDLE_BYTES = 64                                    # WMD_IPC_HANDLE_BYTES
+MAX_FANOUT = 7                                           # WMD_MAX_FANOUT
 
 # name -> (restype, argtypes); mirrors include/wmd_b200.h one to one
 SIGNATURES = {
@@ -55,6 +57,10 @@ SIGNATURES = {
                                              ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, c_i64p, c_f64p]),
     "wmd_emd_batch_host": (ctypes.c_int, [c_handle, c_f64p, c_f64p, c_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_double, c_f64p]),
+    "wmd_peer_alloc": (ctypes.c_int, [c_handle, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "wmd_peer_open": (ctypes.c_int, [c_handle, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "wmd_peer_close": (ctypes.c_int, [c_handle, ctypes.c_void_p, ctypes.c_int32]),
+    "wmd_set_fanout": (ctypes.c_int, [c_handle, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "wmd_set_profiling": (ctypes.c_int, [c_handle, ctypes.c_int32]),
     "wmd_set_serial": (ctypes.c_int, [c_handle, ctypes.c_int32]),
     "wmd_set_distance_table": (ctypes.c_int, [c_handle, ctypes.c_int32]),

@@ -56,6 +56,29 @@ __device__ __forceinline__ int64_t slot_off(const DocSide &s, int64_t tokbase, i
     return s.sel ? (int64_t)q * s.slot : start - tokbase;
 }
 
+// Multi-GPU gather fused into the kernels (wmd_set_fanout): every score / status a pair entry stores ALSO goes to the same
+// pair index of up to kMaxFan further arrays -- the peers' copies of the global result, mapped over NVLink -- so that the
+// ranks of a sharded job need no all-gather of the scores, only a barrier.  Stores are fire-and-forget: the transfer
+// overlaps the solves pair by pair.
+constexpr int kMaxFan = 7;
+struct OutFan {
+    int32_t n = 0;                    // default: off (argument structs are filled field by field)
+    int32_t _pad = 0;
+    double *out[kMaxFan] = {};
+    int32_t *status[kMaxFan] = {};
+};
+// (statically indexed: a run-time index into kernel parameters would copy the whole struct to local memory)
+__device__ __forceinline__ void fan_score(const OutFan &F, int64_t p, double v)
+{
+#pragma unroll
+    for (int k = 0; k < kMaxFan; ++k) if (k < F.n) F.out[k][p] = v;
+}
+__device__ __forceinline__ void fan_status(const OutFan &F, int64_t p, int s)
+{
+#pragma unroll
+    for (int k = 0; k < kMaxFan; ++k) if (k < F.n) F.status[k][p] = s;
+}
+
 struct Vocab {
     const float *table;       // [V, ld] float32, device
     int64_t V;

@@ -35,6 +35,7 @@ struct FusedArgs {
     unsigned long long *stats;        // [6], as PairWork::stats
     double *out;
     int32_t *status;
+    OutFan fan;                       // further copies of out / status (peers of a sharded job)
 };
 
 constexpr int kFusedScratchInts = 6 * 32 + 32 + 2 * 64;      // nBOW scratch: 6 key/row/count arrays, partner map, two FP64 sequences
@@ -87,7 +88,8 @@ __device__ __forceinline__ void fused_side(const DocSide &s, const Vocab &vc, in
     cnt_o = mine ? sc[lane] : 0;
 }
 
-template <int MINB>
+// FAN: the instance that also stores into the peers' arrays (wmd_set_fanout); the single-GPU instance carries none of it
+template <int MINB, bool FAN>
 __global__ void __launch_bounds__(128, MINB)
 wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
 {
@@ -129,12 +131,12 @@ wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
         fused_side(A.s2, A.vc, a2, n2raw, lane, sk2, sr2, sc2, K2, R2, C2, u2, n2);
         (void)K2;
         if (n1 == 0 || n2 == 0) {                                    // S1
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 1; }
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 1; if (FAN) { fan_score(A.fan, p, kInf); fan_status(A.fan, p, 1); } }
             st_tok += n1raw + n2raw;
             continue;
         }
         if (u1 == 1 && u2 == 1 && __shfl_sync(kFull, R1, 0) == __shfl_sync(kFull, R2, 0)) {      // S2
-            if (lane == 0) { A.out[p] = 0.0; A.status[p] = 2; }
+            if (lane == 0) { A.out[p] = 0.0; A.status[p] = 2; if (FAN) { fan_score(A.fan, p, 0.0); fan_status(A.fan, p, 2); } }
             st_tok += n1raw + n2raw;
             continue;
         }
@@ -227,7 +229,7 @@ wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
             mx = __reduce_max_sync(kFull, mx);
         }
         if (mx == 0) {                                               // S4: all-zero distance matrix
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; if (FAN) { fan_score(A.fan, p, kInf); fan_status(A.fan, p, 3); } }
             __syncwarp();
             continue;
         }
@@ -279,6 +281,7 @@ wmd_fused_small_kernel(const __grid_constant__ FusedArgs A)
             dist = __dadd_rn(dist, __dmul_rn(keep[1], maxc_d));
             A.out[p] = dist;
             A.status[p] = 0;
+            if (FAN) { fan_score(A.fan, p, dist); fan_status(A.fan, p, 0); }
         }
         __syncwarp();
     }

@@ -25,6 +25,7 @@ struct PairWork {
     double *wt1, *wt2;                // WMD_MODE_EXACT: nBOW weights count/len per token slot (else unused)
     int32_t exact;                    // != 0: no cancellation / quantisation, weights out, every pair class A
     int32_t _pad;
+    OutFan fan;                       // further copies of out / status (wmd_set_fanout; pyemd mode only)
 };
 
 // Unique in-vocabulary rows of one document, sorted by key. All lanes return (u, nvalid).
@@ -126,11 +127,11 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
 
         int meta = kClsNone;
         if (n1 == 0 || n2 == 0) {                                        // S1
-            if (lane == 0) { out[p] = __longlong_as_double(0x7ff0000000000000LL); status[p] = 1; w.u12[q] = 0; w.meta[q] = 0; }
+            if (lane == 0) { out[p] = __longlong_as_double(0x7ff0000000000000LL); status[p] = 1; w.u12[q] = 0; w.meta[q] = 0; fan_score(w.fan, p, __longlong_as_double(0x7ff0000000000000LL)); fan_status(w.fan, p, 1); }
             continue;
         }
         if (u1 == 1 && u2 == 1 && srow1[0] == srow2[0]) {                // S2
-            if (lane == 0) { out[p] = 0.0; status[p] = 2; w.u12[q] = 0; w.meta[q] = 0; }
+            if (lane == 0) { out[p] = 0.0; status[p] = 2; w.u12[q] = 0; w.meta[q] = 0; fan_score(w.fan, p, 0.0); fan_status(w.fan, p, 2); }
             continue;
         }
         // S5: nBOW weights
@@ -197,6 +198,7 @@ nbow_pairs_kernel(DocSide s1, DocSide s2, Vocab vc, int64_t p0, int32_t npairs, 
             w.pqn[q] = PQn;
             w.extra[q] = __dsub_rn(maxSum, minSum);
             status[p] = 0;
+            fan_status(w.fan, p, 0);
         }
         st_unq += u1 + u2; st_cells += (unsigned long long)u1 * u2; st_solved += 1;
         st_mr = max(st_mr, m); st_mc = max(st_mc, nc);

@@ -48,6 +48,7 @@ struct SolveArgs {
     int64_t V;
     const int32_t *rows1, *rows2;
     float *maxc_w;
+    OutFan fan;                       // further copies of out / status (peers of a sharded job)
 };
 
 // Reads of the word-distance table are single-use 32-byte sectors scattered over V x V floats: they bypass L1 and
@@ -304,7 +305,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
             if (lane == 0) A.maxc_w[q] = maxc_f;
         }
         if (!(maxc_f > 0.f)) {                                   // S4: all-zero distance matrix
-            if (lane == 0) { A.out[A.p0 + q] = __longlong_as_double(0x7ff0000000000000LL); A.status[A.p0 + q] = 3; }
+            if (lane == 0) { A.out[A.p0 + q] = __longlong_as_double(0x7ff0000000000000LL); A.status[A.p0 + q] = 3; fan_score(A.fan, A.p0 + q, __longlong_as_double(0x7ff0000000000000LL)); fan_status(A.fan, A.p0 + q, 3); }
             continue;
         }
         long long opt = 0;
@@ -388,6 +389,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
             dist = __ddiv_rn(dist, Cn);
             dist = __dadd_rn(dist, __dmul_rn(A.extra[q], maxc_d));
             A.out[A.p0 + q] = dist;
+            fan_score(A.fan, A.p0 + q, dist);
         }
         __syncwarp();
     }

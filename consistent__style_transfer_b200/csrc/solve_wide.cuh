@@ -354,7 +354,7 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
         if (GATHER) { r1 = A.rows1 + o1; r2 = A.rows2 + o2; }
         float maxc_f = GATHER ? 0.f : A.maxc[q];
         if (!GATHER && !(maxc_f > 0.f)) {                            // S4: all-zero distance matrix
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; fan_score(A.fan, p, kInf); fan_status(A.fan, p, 3); }
             continue;
         }
         const int32_t *ipR = swap ? A.ip2 + o2 : A.ip1 + o1;         // supplying side
@@ -471,7 +471,7 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
             }
         }
         if (zero_matrix) {                                           // S4: all-zero distance matrix
-            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; }
+            if (lane == 0) { A.out[p] = kInf; A.status[p] = 3; fan_score(A.fan, p, kInf); fan_status(A.fan, p, 3); }
             __syncwarp();
             continue;
         }
@@ -481,6 +481,7 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
             dist = __ddiv_rn(dist, Cn);
             dist = __dadd_rn(dist, __dmul_rn(A.extra[q], (double)maxc_f));
             A.out[p] = dist;
+            fan_score(A.fan, p, dist);
         }
         __syncwarp();
     }

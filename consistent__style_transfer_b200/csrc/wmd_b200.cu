@@ -158,9 +158,11 @@ struct wmd_engine {
     int64_t pending_pairs = -1;                  // pairs of the job in flight between submit and wait (-1: none)
     int host_chunk_first = 32768, host_chunk_max = 131072;  // host jobs in table mode: pairs of the first chunk, cap of the doubling schedule (WMD_HOST_CHUNK=first,max)
     int ap_r1_mult = 3;                          // all-pairs: round 1 solves ap_r1_mult * k candidates per row (WMD_AP_R1MULT)
+    OutFan fan;                                  // wmd_set_fanout: the peers' result arrays (device pointers valid in this process)
     int fused_minb = 9;                          // fused kernel variant: __launch_bounds__(128, 8 / 9 / 10) = 64 / 56 / 48 registers (WMD_FUSED_MINB)
     int fused_blocks_per_sm = 0;                 // fused kernel: resident blocks per SM at the last smem size
     size_t fused_smem_cached = 0;
+    bool fused_fan_cached = false;
     cudaStream_t ap_stream = nullptr;
     DevBuf ap[32];
     unsigned long long *stats = nullptr;        // device [6]
@@ -320,6 +322,7 @@ struct ChunkOut {
     bool solve = true;
     int mode = WMD_MODE_PYEMD;
     bool am_abs = false;                    // device entry: argmins at absolute CSR offsets
+    OutFan fan;                             // pair entries in pyemd mode: further copies of out / status (wmd_set_fanout)
 };
 
 // K2: cost tiles of pairs [p0, p0 + Bc): the planned fast path for pairs that fit a stage, the
@@ -434,7 +437,7 @@ int launch_solvers(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &
     S.s1 = s1; S.s2 = s2; S.p0 = p0; S.npairs = Bc;
     S.ip1 = pw.ip1; S.ip2 = pw.ip2; S.u12 = pw.u12; S.meta = pw.meta; S.pqn = pw.pqn; S.extra = pw.extra;
     S.tiles = tiles; S.tile_stride = tile_stride; S.maxc = W.maxc.as<float>();
-    S.out = O.out; S.status = O.status;
+    S.out = O.out; S.status = O.status; S.fan = O.fan;
     S.list = list; S.nlist = nlist;
     S.D = gather ? E->dtab : nullptr; S.V = E->V; S.rows1 = pw.rows1; S.rows2 = pw.rows2; S.maxc_w = W.maxc.as<float>();
     S.scratch = nullptr;
@@ -530,17 +533,19 @@ int run_chunk_fused(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide 
     F.cap = std::min(32, ML + 1); F.ldc = F.cap | 1; F._pad = 0;
     F.counter = W.counters.as<unsigned int>() + kCtrFused;
     F.biglist = W.biglist.as<int32_t>(); F.nbig = W.counters.as<unsigned int>() + kCtrNBig;
-    F.stats = E->stats; F.out = O.out; F.status = O.status;
+    F.stats = E->stats; F.out = O.out; F.status = O.status; F.fan = O.fan;
     {
         const int wpb = 4;
         const size_t smem = fused_smem_per_warp(F.cap, F.ldc) * wpb;
-        auto kern = E->fused_minb >= 10 ? wmd_fused_small_kernel<10> : E->fused_minb == 9 ? wmd_fused_small_kernel<9> : wmd_fused_small_kernel<8>;
-        if (smem != E->fused_smem_cached) {
+        const bool fan = F.fan.n > 0;
+        auto kern = fan ? wmd_fused_small_kernel<9, true>
+                        : E->fused_minb >= 10 ? wmd_fused_small_kernel<10, false> : E->fused_minb == 9 ? wmd_fused_small_kernel<9, false> : wmd_fused_small_kernel<8, false>;
+        if (smem != E->fused_smem_cached || fan != E->fused_fan_cached) {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, wpb * 32, smem));
             if (nb < 1) return fail(WMD_ECUDA, "wmd_fused_small_kernel cannot be resident");
-            E->fused_blocks_per_sm = nb; E->fused_smem_cached = smem;
+            E->fused_blocks_per_sm = nb; E->fused_smem_cached = smem; E->fused_fan_cached = fan;
         }
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)Bc + 8 * wpb - 1) / (8 * wpb), (int64_t)E->sm_count * E->fused_blocks_per_sm));
         Prof pr(E, WMD_K_FUSED, st);
@@ -557,7 +562,7 @@ int run_chunk_fused(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide 
     pw.rows1 = W.rows1.as<int32_t>(); pw.cnt1 = W.cnt1.as<int32_t>(); pw.ip1 = W.ip1.as<int32_t>();
     pw.rows2 = W.rows2.as<int32_t>(); pw.cnt2 = W.cnt2.as<int32_t>(); pw.ip2 = W.ip2.as<int32_t>();
     pw.u12 = W.u12.as<int32_t>(); pw.meta = W.meta.as<int32_t>(); pw.pqn = W.pqn.as<double>(); pw.extra = W.extra.as<double>();
-    pw.stats = E->stats; pw.exact = 0; pw._pad = 0; pw.wt1 = nullptr; pw.wt2 = nullptr;
+    pw.stats = E->stats; pw.exact = 0; pw._pad = 0; pw.wt1 = nullptr; pw.wt2 = nullptr; pw.fan = O.fan;
     const int32_t *list = W.biglist.as<int32_t>();
     const unsigned int *nlist = W.counters.as<unsigned int>() + kCtrNBig;
     if ((rc = launch_nbow_pairs(E, st, s1, s2, p0, Bc, ML, pw, O, list, nlist))) return rc;
@@ -590,6 +595,7 @@ int run_chunk(wmd_engine *E, Workspace &W, cudaStream_t st, const DocSide &s1, c
     pw.u12 = W.u12.as<int32_t>(); pw.meta = W.meta.as<int32_t>(); pw.pqn = W.pqn.as<double>(); pw.extra = W.extra.as<double>();
     pw.stats = E->stats;
     pw.exact = O.mode == WMD_MODE_EXACT; pw._pad = 0; pw.wt1 = nullptr; pw.wt2 = nullptr;
+    if (!pw.exact && O.solve && !O.rwmd) pw.fan = O.fan;
     if (pw.exact) {
         if ((rc = W.wt1.ensure((size_t)tokcap1 * 8)) || (rc = W.wt2.ensure((size_t)tokcap2 * 8))) return rc;
         pw.wt1 = W.wt1.as<double>(); pw.wt2 = W.wt2.as<double>();
@@ -748,6 +754,10 @@ int enqueue_host_job(wmd_engine *E, const HostJob &J)
         s2.ids = W.ids2.as<int32_t>() - J.off2[c0]; s2.off = W.off2.as<int64_t>();
         ChunkOut O;
         O.out = W.out.as<double>(); O.status = W.status.as<int32_t>(); O.solve = J.solve; O.rwmd = J.rwmd; O.mode = J.mode;
+        if (J.solve && !J.rwmd && J.mode == WMD_MODE_PYEMD) {        // the chunk's kernels index from 0: the peers' arrays start at the chunk
+            O.fan = E->fan;
+            for (int k = 0; k < O.fan.n; ++k) { O.fan.out[k] += c0; O.fan.status[k] += c0; }
+        }
         if (J.rwmd) {
             if ((rc = W.lb.ensure((size_t)Bc * 8)) || (rc = W.l1.ensure((size_t)Bc * 8)) || (rc = W.l2.ensure((size_t)Bc * 8)) ||
                 (rc = W.am1.ensure((size_t)std::max<int64_t>(t1, 1) * 4)) || (rc = W.am2.ensure((size_t)std::max<int64_t>(t2, 1) * 4)))
@@ -872,6 +882,7 @@ int run_dev_pairs(wmd_engine *E, const DocSide &s1, const DocSide &s2, int64_t t
     if (!out && npairs > 0) return fail(WMD_EINVAL, "out is null");
     ChunkOut O;
     O.out = out; O.status = status; O.mode = mode;
+    if (mode == WMD_MODE_PYEMD && status) O.fan = E->fan;         // indexed like out / status (scratch status has no peers)
     return run_dev_job(E, s1, s2, total1, total2, ml1, ml2, npairs, O, us);
 }
 
@@ -1425,6 +1436,67 @@ int wmd_pairs_wait(wmd_handle E, double *out, int32_t *status)
     const double *po = static_cast<const double *>(E->pin_out);
     memcpy(out, po, (size_t)n * 8);
     if (status) memcpy(status, po + n, (size_t)n * 4);
+    return WMD_OK;
+}
+
+int wmd_set_fanout(wmd_handle E, int32_t n, double *const *out_ptrs, int32_t *const *status_ptrs)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (n < 0 || n > kMaxFan) return fail(WMD_EINVAL, "fan-out of %d arrays; the limit is %d", (int)n, kMaxFan);
+    if (n > 0 && (!out_ptrs || !status_ptrs)) return fail(WMD_EINVAL, "null fan-out pointers");
+    OutFan F;
+    F.n = n;
+    for (int k = 0; k < n; ++k) {
+        if (!out_ptrs[k] || !status_ptrs[k]) return fail(WMD_EINVAL, "fan-out array %d is null", k);
+        F.out[k] = out_ptrs[k]; F.status[k] = status_ptrs[k];
+    }
+    E->fan = F;
+    return WMD_OK;
+}
+
+int wmd_peer_alloc(wmd_handle E, int64_t bytes, void **dev_ptr, unsigned char *ipc_handle)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (bytes <= 0 || !dev_ptr || !ipc_handle) return fail(WMD_EINVAL, "bad arguments");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == WMD_IPC_HANDLE_BYTES, "WMD_IPC_HANDLE_BYTES");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return fail(WMD_ENOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    if ((e = cudaMemset(p, 0, (size_t)bytes)) != cudaSuccess || (e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) {
+        cudaFree(p);
+        return fail(WMD_ECUDA, "peer buffer: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &h, sizeof h);
+    *dev_ptr = p;
+    return WMD_OK;
+}
+
+int wmd_peer_open(wmd_handle E, const unsigned char *ipc_handle, void **dev_ptr)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (!ipc_handle || !dev_ptr) return fail(WMD_EINVAL, "bad arguments");
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(WMD_ECUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    *dev_ptr = p;
+    return WMD_OK;
+}
+
+int wmd_peer_close(wmd_handle E, void *dev_ptr, int32_t opened)
+{
+    if (!E) return fail(WMD_EINVAL, "null handle");
+    if (!dev_ptr) return WMD_OK;
+    int rc;
+    if ((rc = set_device(E))) return rc;
+    const cudaError_t e = opened ? cudaIpcCloseMemHandle(dev_ptr) : cudaFree(dev_ptr);
+    if (e != cudaSuccess) return fail(WMD_ECUDA, "%s failed: %s", opened ? "cudaIpcCloseMemHandle" : "cudaFree", cudaGetErrorString(e));
     return WMD_OK;
 }
 

@@ -154,6 +154,35 @@ class WMDEngine:
         _lib.check(self._L.wmd_pairs_wait(self._handle(), _ptr(out, c_f64p), _ptr(status, c_i32p)))
         return out, status
 
+    # -- multi-GPU: the score gather fused into the kernels (sharding.PeerScores drives these) --------
+    def peer_alloc(self, nbytes: int):
+        """A zero-filled device buffer the other ranks of the box can map -> (device pointer, CUDA IPC handle bytes)."""
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(self._L.wmd_peer_alloc(self._handle(), int(nbytes), ctypes.byref(ptr), handle))
+        return int(ptr.value), handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        _lib.check(self._L.wmd_peer_open(self._handle(), bytes(handle), ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int, opened: bool):
+        _lib.check(self._L.wmd_peer_close(self._handle(), ctypes.c_void_p(ptr), int(bool(opened))))
+
+    def set_fanout(self, out_ptrs: Sequence[int] = (), status_ptrs: Sequence[int] = ()):
+        """Every score / status the pair entries store at pair index p from now on also goes to out_ptrs[k] + 8 p /
+        status_ptrs[k] + 4 p (device pointers on this engine's device); no arguments: off."""
+        n = len(out_ptrs)
+        if n != len(status_ptrs):
+            raise ValueError("one status array per score array")
+        if n == 0:
+            _lib.check(self._L.wmd_set_fanout(self._handle(), 0, None, None))
+            return
+        o = (ctypes.c_void_p * n)(*[int(x) for x in out_ptrs])
+        t = (ctypes.c_void_p * n)(*[int(x) for x in status_ptrs])
+        _lib.check(self._L.wmd_set_fanout(self._handle(), n, o, t))
+
     def workspace_bytes(self, npairs: int, max_len1: int, max_len2: int):
         """(upper estimate of the device bytes a pair call of that size needs, bytes the handle holds now)"""
         est = ctypes.c_int64(); res = ctypes.c_int64()

@@ -147,14 +147,97 @@ def gather_scores(local_out, local_status, bounds: np.ndarray, group=None):
     return out, st
 
 
+class PeerScores:
+    """The global result of a sharded pair job, resident on every rank and filled by the ranks' KERNELS: each rank's
+    pair entries store every score / status straight into the peers' copies over NVLink (``WMDEngine.set_fanout``),
+    so the job needs no all-gather after the kernels -- the stores overlap the solves -- only a barrier before the
+    result is read.  One process per GPU on one box (CUDA IPC); two buffer sets are used in turn, so a rank may start
+    its next job while a peer still reads the previous result on its stream.
+
+        peer = PeerScores(engine, total_pairs)                 # collective: every rank of the group
+        out, st, (lo, hi) = wmd_pairs_sharded(engine.wmd_pairs_torch, ids1, off1, ids2, off2, peer=peer)
+        peer.close()
+    """
+
+    SETS = 2
+
+    def __init__(self, engine, total: int, group=None):
+        import torch
+        dist = _dist()
+        if dist is None:
+            raise RuntimeError("PeerScores needs an initialised torch.distributed process group")
+        self.engine, self.total, self.group = engine, int(total), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world - 1 > 7:
+            raise RuntimeError("the fan-out holds at most 7 peers")
+        self.dev = torch.device("cuda", engine.device)
+        self.stride = ((12 * self.total + 255) // 256) * 256          # one set: float64 scores, then int32 status
+        self.base, handle = engine.peer_alloc(self.SETS * self.stride)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.peer_base = [self.base if r == self.rank else engine.peer_open(handles[r]) for r in range(self.world)]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._turn = 0
+        self._views = [self._wrap(k) for k in range(self.SETS)]
+        dist.barrier(group=group)
+
+    def _wrap(self, k: int):
+        import torch
+
+        class _Mem:                                                      # torch.as_tensor reads __cuda_array_interface__
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 2}
+        b = self.base + k * self.stride
+        out = torch.as_tensor(_Mem(b, (self.total,), "<f8"), device=self.dev)
+        st = torch.as_tensor(_Mem(b + 8 * self.total, (self.total,), "<i4"), device=self.dev)
+        return out, st
+
+    def begin(self, lo: int):
+        """Points the engine's fan-out at the peers' copies of the set in turn, advanced to this rank's first pair;
+        returns this rank's own (out, status) tensors of that set."""
+        k = self._turn
+        outs = [b + k * self.stride + 8 * lo for r, b in enumerate(self.peer_base) if r != self.rank]
+        sts = [b + k * self.stride + 8 * self.total + 4 * lo for r, b in enumerate(self.peer_base) if r != self.rank]
+        self.engine.set_fanout(outs, sts)
+        return self._views[k]
+
+    def end(self):
+        """Fan-out off, and the cross-rank barrier (stream-ordered: one tiny NCCL all-reduce) after which every rank's
+        copy of the set is complete."""
+        dist = _dist()
+        self.engine.set_fanout()
+        dist.all_reduce(self._flag, group=self.group)
+        out, st = self._views[self._turn]
+        self._turn = (self._turn + 1) % self.SETS
+        return out, st
+
+    def close(self):
+        import torch
+        dist = _dist()
+        torch.cuda.synchronize(self.dev)
+        if dist is not None:
+            dist.barrier(group=self.group)
+        self._views = []
+        for r, b in enumerate(self.peer_base):
+            if r != self.rank:
+                self.engine.peer_close(b, True)
+        if dist is not None:
+            dist.barrier(group=self.group)                               # nobody still maps the buffer we free
+        self.engine.peer_close(self.base, False)
+        self.peer_base = []
+
+
 def wmd_pairs_sharded(score_fn: Callable, ids1, off1, ids2, off2, group=None, gather: bool = True,
-                      rank: Optional[int] = None, world: Optional[int] = None, balance: str = "tokens"):
+                      rank: Optional[int] = None, world: Optional[int] = None, balance: str = "tokens",
+                      peer: Optional["PeerScores"] = None):
     """Every rank passes the SAME full CSR batch (host numpy); rank r scores its contiguous slice with
     ``score_fn(ids1, off1_slice, ids2, off2_slice) -> (float64 tensor, int32 tensor)`` (e.g.
     ``engine.wmd_pairs_torch``; the offset slices are views that keep pointing into the full id arrays, nothing is
     copied) and, with ``gather``, every rank receives all scores in input order.  ``balance``: "tokens" (slices of
     equal token count, found by binary search on the offsets) or "cost" (the quadratic per-pair model of
-    ``pair_cost``, one pass over the batch).  Returns (out, status, (lo, hi))."""
+    ``pair_cost``, one pass over the batch).  With ``peer`` (a ``PeerScores`` of the batch's size) the gather is fused
+    into the kernels: ``score_fn`` must accept ``out=`` / ``status=`` tensors (``engine.wmd_pairs_torch`` does) and the
+    returned tensors are the rank's resident copy of the global result.  Returns (out, status, (lo, hi))."""
     dist = _dist()
     if world is None:
         world = dist.get_world_size(group) if dist else 1
@@ -163,6 +246,13 @@ def wmd_pairs_sharded(score_fn: Callable, ids1, off1, ids2, off2, group=None, ga
     off1 = np.asarray(off1, np.int64); off2 = np.asarray(off2, np.int64)
     bounds = partition_by_tokens(off1, off2, world) if balance == "tokens" else partition(pair_cost(off1, off2), world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    if peer is not None:
+        g_out, g_st = peer.begin(lo)
+        try:
+            score_fn(ids1, off1[lo:hi + 1], ids2, off2[lo:hi + 1], out=g_out[lo:hi], status=g_st[lo:hi])
+        finally:
+            out, st = peer.end()
+        return out, st, (lo, hi)
     out, st = score_fn(ids1, off1[lo:hi + 1], ids2, off2[lo:hi + 1])
     if gather:
         out, st = gather_scores(out, st, bounds, group=group)

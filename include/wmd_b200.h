@@ -208,6 +208,29 @@ int wmd_distance_table_info(wmd_handle h, int64_t *bytes, double *build_ms, int3
 int wmd_workspace_bytes(wmd_handle h, int64_t npairs, int32_t max_len1, int32_t max_len2,
                         int64_t *estimate, int64_t *resident);
 
+/* multi-GPU: the score gather fused into the kernels -------------------------------------------
+ * Not in the reference (single GPU, /root/reference/job.yaml:29-32).  SURVEY.md 8(e): pairs are independent, the only
+ * exchange of a sharded job is the gather of the final scores; instead of an all-gather after the kernels, every
+ * rank's kernels store each score / status straight into the peers' copies of the global result over NVLink
+ * (fire-and-forget stores that overlap the solves), and the ranks only need a barrier before reading. */
+
+#define WMD_IPC_HANDLE_BYTES 64
+#define WMD_MAX_FANOUT 7
+
+/* A device buffer other processes of the same box can map: cudaMalloc + zero fill, its CUDA IPC handle in
+ * ipc_handle[WMD_IPC_HANDLE_BYTES] (hand it to the peers by any means, e.g. torch.distributed.all_gather_object). */
+int wmd_peer_alloc(wmd_handle h, int64_t bytes, void **dev_ptr, unsigned char *ipc_handle);
+/* Maps a peer's buffer into this process (peer access is enabled on first use); *dev_ptr is valid on h's device. */
+int wmd_peer_open(wmd_handle h, const unsigned char *ipc_handle, void **dev_ptr);
+/* opened != 0: unmaps a buffer of wmd_peer_open; 0: frees a buffer of wmd_peer_alloc. */
+int wmd_peer_close(wmd_handle h, void *dev_ptr, int32_t opened);
+/* From now on every score / status the pair entries (wmd_pairs_dev, wmd_pairs_padded_dev, wmd_pairs_host,
+ * wmd_pairs_host_in_dev_out; WMD_MODE_PYEMD) store at pair index p ALSO goes to out_ptrs[k][p] / status_ptrs[k][p],
+ * k < n <= WMD_MAX_FANOUT (device pointers valid on h's device, e.g. from wmd_peer_open, already advanced to this rank's
+ * first pair).  n == 0 switches it off.  The calls stay stream-ordered; a cross-rank barrier after them makes the peers'
+ * copies complete. */
+int wmd_set_fanout(wmd_handle h, int32_t n, double *const *out_ptrs, int32_t *const *status_ptrs);
+
 /* instrumentation ----------------------------------------------------------------------------- */
 
 /* When enabled, every kernel launch is bracketed by CUDA events on its own stream. */

@@ -34,6 +34,22 @@ def _worker(rank, world, port, q):
         ids1, off1, ids2, off2 = workload.make_pairs(90_000, "uniform:1-40", "independent", V=V, seed=9)
         out, st, (lo, hi) = sharding.wmd_pairs_sharded(eng.wmd_pairs_torch, ids1, off1, ids2, off2)
         torch.cuda.synchronize()
+        # the same job with the gather fused into the kernels: peer stores over NVLink, no all-gather; three jobs in a row
+        # through the two buffer sets, host entry and device entry, documents above 32 tokens included (every kernel family)
+        peer = sharding.PeerScores(eng, 90_000)
+        p_out = p_st = None
+        for it in range(3):
+            if it == 1:                                                   # device-resident slice through wmd_pairs_cuda
+                d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in
+                     (ids1[off1[lo]:off1[hi]], off1[lo:hi + 1] - off1[lo], ids2[off2[lo]:off2[hi]], off2[lo:hi + 1] - off2[lo])]
+                fn = lambda a, b, c, e, out=None, status=None: eng.wmd_pairs_cuda(d[0], d[1], d[2], d[3], 40, 40, out=out, status=status)
+            else:
+                fn = eng.wmd_pairs_torch
+            p_out, p_st, (plo, phi) = sharding.wmd_pairs_sharded(fn, ids1, off1, ids2, off2, peer=peer)
+            assert (plo, phi) == (lo, hi)
+            torch.cuda.synchronize()
+            assert torch.equal(p_out, out) and torch.equal(p_st, st), f"peer gather differs in job {it}"
+        peer.close()
         # all-pairs: this rank's row block, result left on the device, all-gathered over NCCL
         docs, doff, _, _ = workload.make_pairs(700, "yelp", "independent", V=V, seed=10)
         blocks = sharding.row_blocks(700, world)
