@@ -449,19 +449,33 @@ emd_solve_wide_kernel(const __grid_constant__ SolveArgs A)
                 // quantised costs of the residual sub-tile (S6(d)); the dummy row / column costs 0
                 const float *tile = GATHER ? nullptr : A.tiles + (int64_t)q * A.tile_stride;
                 __syncwarp();
-                for (int rI = 0; rI < mm; ++rI) {
-                    const int i = rI < nrow ? rowL[rI] & 0xff : 0;
+                constexpr int QB = KC <= 2 ? 8 : KC <= 4 ? 4 : 2;    // rows in flight: the values come back from L2 or DRAM
+                for (int r0 = 0; r0 < mm; r0 += QB) {
+                    float dv[QB][KC];
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) {
-                        const int c = lane + 32 * k;
-                        int ic = 0;
-                        if (c < ncol && rI < nrow) {
-                            float dv;
-                            if (GATHER) dv = __int_as_float(cost[rI * ldc + c]);
-                            else dv = rows_doc1 ? tile[(int64_t)i * u2 + cj[k]] : tile[(int64_t)cj[k] * u2 + i];
-                            ic = (int)floor(__dadd_rn(__dmul_rn((double)dv, Cn), 0.5));
+                    for (int b = 0; b < QB; ++b) {
+                        const int rI = min(r0 + b, mm - 1);
+                        const int i = rI < nrow ? rowL[rI] & 0xff : 0;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            dv[b][k] = 0.f;
+                            if (c < ncol && rI < nrow) {
+                                if (GATHER) dv[b][k] = __int_as_float(cost[rI * ldc + c]);
+                                else dv[b][k] = rows_doc1 ? tile[(int64_t)i * u2 + cj[k]] : tile[(int64_t)cj[k] * u2 + i];
+                            }
                         }
-                        if (c < ncc) cost[rI * ldc + c] = ic;
+                    }
+#pragma unroll
+                    for (int b = 0; b < QB; ++b) {
+                        const int rI = r0 + b;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            int ic = 0;
+                            if (c < ncol && rI < nrow) ic = (int)floor(__dadd_rn(__dmul_rn((double)dv[b][k], Cn), 0.5));
+                            if (c < ncc && rI < mm) cost[rI * ldc + c] = ic;
+                        }
                     }
                 }
                 // supplies last: srem does not alias the lists, u and cmask (which do) are cleared by the solver
