@@ -399,7 +399,7 @@ emd_solve_small_kernel(const __grid_constant__ SolveArgs A)
 // WMD_MODE_EXACT: the real-valued transportation optimum in FP64 -- no 1e6 grid, no cancellation
 // (an additive mode: the reference's pyemd never computes it).  Rows = the unique
 // tokens of doc1 with the nBOW weights count/len as supplies, columns = doc2's; costs are the float32
-// distances widened to double.  Same primal-dual method as transport_solve<KC> on doubles; masses
+// distances widened to double.  Same primal-dual method as transport_solve_small on doubles; masses
 // below kExactTol are treated as shipped (the two weight vectors sum to 1 only up to rounding).
 // One warp per pair; cost / flow matrices in L2-resident global scratch, duals and tree in shared memory.
 // ------------------------------------------------------------------------------------------------

@@ -11,8 +11,9 @@
 //     L + 32k, k < KC).  The row side -- potential u, remaining supply, tree predecessor -- the column deficits, the
 //     tree predecessor of every column and cmask[j] (bit rows shipping into column j) sit in shared memory and are
 //     read by broadcast; the tree set is one register per lane (lane w owns rows 32w .. 32w+31).  The row count
-//     therefore costs no registers and no template parameter, and the kernels run at 20 .. 32 warps per SM where
-//     the <KR, KC> register arrays of the previous version allowed 12 .. 16.
+//     therefore costs no registers and no template parameter, and the kernels run at 16 .. 32 warps per SM where
+//     register arrays for both sides (the previous version) allowed 12 .. 16.  The supplies, read once per row, live in
+//     the per-warp global scratch: in shared memory they would cost the 5- and 6-word classes their sixth block per SM.
 //   * a row that joins the tree at distance d gets u -= d at once and every tree row u += D when the search ends
 //     at distance D (same update as u += D - d, no per-row distance array).
 //   * rows that join the tree in one step are relaxed two at a time: both cost rows are requested before either

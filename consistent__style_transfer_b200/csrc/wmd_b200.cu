@@ -1,8 +1,11 @@
 // wmd_b200.cu -- host engine + C ABI of libwmd_b200.so (see include/wmd_b200.h).
 //
-// Pipeline per chunk of pairs (all on one CUDA stream, chunks alternate between two streams so
-// that the FP32-bound cost kernel of one chunk overlaps the latency-bound solver of the other
-// and the chunk's tiles stay L2-resident between the two):
+// Default path (word-distance table resident): one persistent wmd_fused_small_kernel per chunk scores every pair of
+// documents of <= 32 tokens end to end; what it leaves behind goes through list-mode nbow_pairs_kernel, list_sort_kernel
+// (longest first) and the solver classes -- emd_solve_small_kernel and emd_solve_wide_kernel<1 .. 8> side by side on
+// their own streams -- which read their costs from the same table.
+// Direct path per chunk of pairs (chunks alternate between two streams so that the FP32-bound cost kernel of one chunk
+// overlaps the latency-bound solver of the other and the chunk's tiles stay L2-resident between the two):
 //     K1 nbow_pairs_kernel -> K2 cost_plan_kernel + cost_tiles_fast_kernel -> K3 emd_solve_small_kernel / emd_solve_wide_kernel
 // There is no CPU implementation behind this ABI: without a device every entry fails.
 #include "../../include/wmd_b200.h"
