@@ -172,10 +172,34 @@ class PeerScores:
             raise RuntimeError("the fan-out holds at most 7 peers")
         self.dev = torch.device("cuda", engine.device)
         self.stride = ((12 * self.total + 255) // 256) * 256          # one set: float64 scores, then int32 status
-        self.base, handle = engine.peer_alloc(self.SETS * self.stride)
+        # Every step below is collective-safe: a rank that fails still takes part in the exchanges, and then all ranks raise.
+        self.base, handle, err = 0, None, None
+        try:
+            self.base, handle = engine.peer_alloc(self.SETS * self.stride)
+        except RuntimeError as exc:
+            err = exc
         handles = [None] * self.world
         dist.all_gather_object(handles, handle, group=group)
-        self.peer_base = [self.base if r == self.rank else engine.peer_open(handles[r]) for r in range(self.world)]
+        self.peer_base = [0] * self.world
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r in range(self.world):
+                    self.peer_base[r] = self.base if r == self.rank else engine.peer_open(handles[r])
+            except RuntimeError as exc:
+                err = exc
+        elif err is None:
+            err = RuntimeError("a peer could not allocate its result buffer")
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            for r, b in enumerate(self.peer_base):
+                if b and r != self.rank:
+                    engine.peer_close(b, True)
+            dist.barrier(group=group)
+            if self.base:
+                engine.peer_close(self.base, False)
+            self.peer_base = []
+            raise RuntimeError(f"PeerScores: peer mapping unavailable ({err or 'on another rank'})")
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._turn = 0
         self._views = [self._wrap(k) for k in range(self.SETS)]
