@@ -31,6 +31,10 @@ CONFIGS = [
     ("uniform:1-100", "independent", 200, 300, False, 0.01),
     ("uniform:20-200", "noised", 600, 20, True, 0.0),
     ("uniform:33-64", "independent", 64, 48, False, 0.0),
+    # every wide solver class, both orientations, the 257-row case (solve_wide.cuh)
+    ("uniform:1-256", "independent", 10_000, 300, False, 0.0),
+    ("fixed:256", "independent", 700, 16, True, 0.0),
+    ("uniform:100-200", "noised", 3_000, 64, False, 0.01),
 ]
 bad = 0
 for shape, variant, V, d, use_rank, oov in CONFIGS:
