@@ -416,3 +416,61 @@ def test_distance_table_policy_follows_the_budget(eng_mod, monkeypatch):
     assert not e.distance_table_info()["resident"]
     assert a.tobytes() == b.tobytes() and np.array_equal(sa, sb)
     e.close()
+
+
+def test_fanout_duplicates_scores_and_status(eng_mod, dtab):
+    """wmd_set_fanout on ONE GPU: every kernel family that stores a score or a status (fused kernel, list-mode nBOW,
+    class A, wide classes; direct-path K1 / K3) must store the same value into the extra arrays -- the multi-GPU gather
+    (sharding.PeerScores) rests on exactly this; two-rank coverage is in test_gpu_multirank.py."""
+    import torch
+    V = 900
+    table = workload.make_table(V, 40, seed=8)
+    table[11] = table[10]
+    a1, o1, a2, o2 = workload.make_pairs(6000, "uniform:1-90", "independent", V=V, seed=4)        # short, long, wide classes
+    docs1 = [[-1], [5], [10], [1, 2], []]; docs2 = [[1], [5], [11], [2, 1], [3]]                   # S1, S2, S4, zero distance, empty
+    b1, p1 = workload.to_csr(docs1); b2, p2 = workload.to_csr(docs2)
+    ids1 = np.concatenate([a1, b1]); off1 = np.concatenate([o1, o1[-1] + p1[1:]])
+    ids2 = np.concatenate([a2, b2]); off2 = np.concatenate([o2, o2[-1] + p2[1:]])
+    B = len(off1) - 1
+    e = eng_mod.WMDEngine(table, distance_table=dtab)
+    want, wst = e.wmd_pairs(ids1, off1, ids2, off2)
+    dev = torch.device("cuda", e.device)
+    # two extra copies, device entry
+    x = [(torch.full((B,), -7.0, dtype=torch.float64, device=dev), torch.full((B,), -7, dtype=torch.int32, device=dev)) for _ in range(2)]
+    e.set_fanout([t[0].data_ptr() for t in x], [t[1].data_ptr() for t in x])
+    d = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (ids1.astype(np.int32), off1, ids2.astype(np.int32), off2)]
+    out, st = e.wmd_pairs_cuda(d[0], d[1], d[2], d[3], 90, 90)
+    torch.cuda.synchronize()
+    for o, s in x:
+        assert torch.equal(o, out) and torch.equal(s, st)
+    assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(st.cpu().numpy(), wst)
+    # host entry (chunked: the extra arrays are addressed per chunk), then off again
+    for o, s in x:
+        o.fill_(-7.0); s.fill_(-7)
+    got, gst = e.wmd_pairs(ids1, off1, ids2, off2)
+    torch.cuda.synchronize()
+    for o, s in x:
+        assert np.array_equal(o.cpu().numpy(), want) and np.array_equal(s.cpu().numpy(), wst)
+    e.set_fanout()
+    for o, s in x:
+        o.fill_(-7.0); s.fill_(-7)
+    e.wmd_pairs(ids1, off1, ids2, off2)
+    torch.cuda.synchronize()
+    assert float(x[0][0].max()) == -7.0 and int(x[0][1].max()) == -7
+    with pytest.raises(RuntimeError):
+        e.set_fanout([0] * 8, [0] * 8)                                     # more than WMD_MAX_FANOUT arrays
+    # a peer buffer of this handle: alloc, use as a fan-out target, free
+    ptr, handle = e.peer_alloc(12 * B)
+    assert ptr != 0 and len(handle) == 64
+    e.set_fanout([ptr], [ptr + 8 * B])
+    e.wmd_pairs(ids1, off1, ids2, off2)
+    e.set_fanout()
+    torch.cuda.synchronize()
+
+    class _Mem:
+        def __init__(self, p, shape, typestr):
+            self.__cuda_array_interface__ = {"data": (p, False), "shape": shape, "typestr": typestr, "version": 2}
+    po = torch.as_tensor(_Mem(ptr, (B,), "<f8"), device=dev).clone(); ps = torch.as_tensor(_Mem(ptr + 8 * B, (B,), "<i4"), device=dev).clone()
+    assert np.array_equal(po.cpu().numpy(), want) and np.array_equal(ps.cpu().numpy(), wst)
+    e.peer_close(ptr, False)
+    e.close()
