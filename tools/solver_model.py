@@ -6,6 +6,7 @@ per-SASS-instruction execution counts ncu reports for the kernel (70.3 selection
 before the orientation change), so a variant can be judged without GPU time.
 
     python tools/solver_model.py [pairs]
+    python tools/solver_model.py --long [pairs]      # long documents: fixed 256 tokens against mixed lengths 1 .. 256
 
 Variants reported: rows = supplying side (the original), rows = the side with more nodes (built), the latter
 with searches continuing after intact multi-hop augmentations (built), and on top of that the reduced-cost start with
@@ -104,7 +105,32 @@ def residual_problem(T, a, b):
     return C, s, t
 
 
+def long_documents(npairs):
+    """What the wide solver (solve_wide.cuh) sees: column selections / row relaxations per residual problem, rows = the
+    side with more nodes, for 256-token pairs (near-equal masses: almost assignment problems) and for pairs of mixed
+    lengths (masses 1/n1 against 1/n2: every node needs several partners) -- the reason a mixed batch costs more than
+    the fixed-length runs predict (profiles/README.md)."""
+    T = workload.make_table(10_000, 300, seed=0)
+    for shape in ("fixed:256", "uniform:1-256"):
+        ids1, off1, ids2, off2 = workload.make_pairs(npairs, shape, "independent", V=10_000, seed=1)
+        print(shape)
+        for p in range(npairs):
+            pr = residual_problem(T, ids1[off1[p]:off1[p + 1]], ids2[off2[p]:off2[p + 1]])
+            if pr is None:
+                continue
+            C, s, t = pr
+            if C.shape[0] < C.shape[1]:
+                C, s, t = C.T.copy(), t.copy(), s.copy()
+            if C.shape[0] <= 32:
+                continue
+            _, cnt = solve(C, s, t, True)
+            print(f"  {C.shape[0]:3d} x {C.shape[1]:3d}: searches {cnt[0]:5d}, column selections {cnt[1]:6d}, row relaxations {cnt[2]:6d}")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--long":
+        long_documents(int(sys.argv[2]) if len(sys.argv) > 2 else 8)
+        return
     npairs = int(sys.argv[1]) if len(sys.argv) > 1 else 400
     T = workload.make_table(10_000, 300, seed=0)
     ids1, off1, ids2, off2 = workload.make_pairs(npairs, "yelp", "independent", V=10_000, seed=1)
