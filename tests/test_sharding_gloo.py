@@ -33,6 +33,37 @@ def _worker(rank, world, port, B, q):
             return torch.from_numpy(out), torch.from_numpy(st)
 
         out, st, (lo, hi) = sharding.wmd_pairs_sharded(score, ids1, off1, ids2, off2)
+
+        # the peer= path of the same call (on GPUs: sharding.PeerScores, the kernels store into the peers' copies).  The
+        # stand-in keeps the protocol -- begin(lo) hands out this rank's full-size result, the scorer fills its slice
+        # in place, end() is the barrier -- and plays the peers' stores with one all-reduce of the disjoint slices.
+        class FakePeer:
+            def __init__(self, total):
+                self.out = torch.zeros(total, dtype=torch.float64); self.st = torch.zeros(total, dtype=torch.int32)
+                self.began = None
+
+            def begin(self, lo_):
+                self.began = lo_
+                self.out.zero_(); self.st.zero_()
+                return self.out, self.st
+
+            def end(self):
+                fin = torch.isfinite(self.out)
+                inf_mask = (~fin).to(torch.int32)                          # +inf scores travel as a mask: the sum stays exact
+                dist.all_reduce(inf_mask); dist.all_reduce(self.st)
+                o = torch.where(fin, self.out, torch.zeros_like(self.out)); dist.all_reduce(o)
+                self.out = torch.where(inf_mask > 0, torch.full_like(o, float("inf")), o)
+                return self.out, self.st
+
+        def score_into(a1, o1, a2, o2, out=None, status=None):
+            o, s_ = score(a1, o1, a2, o2)
+            out.copy_(o); status.copy_(s_)
+            return out, status
+
+        peer = FakePeer(B)
+        p_out, p_st, (plo, phi) = sharding.wmd_pairs_sharded(score_into, ids1, off1, ids2, off2, peer=peer)
+        assert (plo, phi) == (lo, hi) and peer.began == lo
+        assert torch.equal(p_out, out) and torch.equal(p_st, st)
         q.put((rank, lo, hi, calls[0], out.numpy().tobytes(), st.numpy().tobytes()))
     finally:
         dist.destroy_process_group()
