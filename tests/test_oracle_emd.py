@@ -64,10 +64,12 @@ def _random_problem(rng, n, density=0.7):
     return c1 / float(c1.sum()), c2 / float(c2.sum()), D
 
 
-@pytest.mark.parametrize("n", [2, 3, 5, 9, 17, 33])
+@pytest.mark.parametrize("n", [2, 3, 5, 9, 17, 33, 96, 200])
 def test_integer_stage_vs_network_simplex(oracle, n):
+    # up to the problem sizes of the GPU's wide solver classes (long documents): the oracle those are checked against
+    # is itself checked against an independent exact solver there
     rng = np.random.default_rng(100 + n)
-    for _ in range(25 if n < 20 else 6):
+    for _ in range(25 if n < 20 else 6 if n < 64 else 2):
         d1, d2, D = _random_problem(rng, n)
         iP, iQ, iC = oracle.emd_quantise(d1, d2, D)
         assert oracle.emd_integral(iP, iQ, iC, 0) == _nx_integer_opt(iP, iQ, iC)
